@@ -1,0 +1,130 @@
+"""CPU tests: the oracle (oracle/pfft_oracle.py) against the golden vectors captured
+from the reference's own compiled integer code (tests/golden/gen_golden.py), against
+the values quoted in SURVEY.md 8c, and -- when the prebuilt oracle/_ref library is
+present -- against that library live."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import pfft_oracle as po
+
+
+def _load(golden_dir, name):
+    with open(os.path.join(golden_dir, name)) as f:
+        return json.load(f)
+
+
+def test_local_block_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "local_block.json")
+    assert len(g["cases"]) > 10000
+    for kind, ni, no, np_, pid, flags, ib, ob, lni, lis, lno, los in g["cases"]:
+        got = po.local_block(kind, ni, no, np_, pid, flags, ib, ob)
+        assert [list(x) for x in got] == [lni, lis, lno, los], (kind, ni, no, np_, pid, flags, ib, ob)
+
+
+def test_local_size_gc_matches_reference_golden(golden_dir):
+    g = _load(golden_dir, "local_size_gc.json")
+    for c in g["cases"]:
+        mem, ngc, gcs = po.local_size_gc(c["local_n"], c["local_start"], c["howmany"], c["gc_below"], c["gc_above"])
+        assert (mem, ngc, gcs) == (c["mem"], c["ngc"], c["gc_start"])
+
+
+def test_init_input_bit_exact(golden_dir):
+    g = _load(golden_dir, "init_input.json")
+    for c in g["cases"]:
+        got = po.init_input(c["kind"], c["n"], c["local_n"], c["local_start"]).ravel()
+        if c["kind"] == "real":
+            want = np.array([float.fromhex(v) for v in c["values"]])
+        else:
+            want = np.array([complex(float.fromhex(a), float.fromhex(b)) for a, b in c["values"]])
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.float64), want.view(np.float64)), c["kind"]
+
+
+def test_survey_quoted_values():
+    # values printed by the reference's own code
+    x = po.init_input("complex", [29, 27, 31], [2, 2, 3], [0, 0, 0]).ravel()
+    assert x[0] == 1500 + 1250j and x[2] == 250 + 200j
+    assert x[3] == complex(15.625, 15.384615384615385)
+    assert po.local_block("c2c", [29, 27, 31], [29, 27, 31], [2, 2], 3, po.TRANSPOSED_OUT) == \
+        ([14, 13, 31], [15, 14, 0], [29, 13, 15], [0, 14, 16])
+    assert po.local_block("r2c", [1024] * 3, [1024] * 3, [2, 4], 7, po.TRANSPOSED_OUT | po.PADDED_R2C) == \
+        ([512, 256, 1026], [512, 768, 0], [1024, 512, 126], [0, 512, 387])
+    assert po.local_block("c2c", [29, 27, 31], [29, 27, 31], [2, 2, 2], 7, po.TRANSPOSED_OUT)[2:] == \
+        ([29, 13, 7], [0, 14, 24])
+    assert po.local_block("c2c", [128] * 4, [128] * 4, [2, 2, 2], 7, po.TRANSPOSED_OUT) == \
+        ([64, 64, 64, 128], [64, 64, 64, 0], [128, 64, 64, 64], [0, 64, 64, 64])
+
+
+def test_live_reference_library_if_present():
+    import refint
+    if not refint.available():
+        pytest.skip("oracle/_ref/libpfft_refint.so not built (needs /root/reference)")
+    ref = refint.RefInt()
+    rng = np.random.default_rng(7)
+    for _ in range(300):
+        d = int(rng.integers(3, 5))
+        n = [int(x) for x in rng.integers(2, 40, size=d)]
+        mesh = [int(x) for x in rng.integers(1, 4, size=int(rng.integers(1, 3)))]
+        kind = ["c2c", "r2c", "c2r", "r2r"][int(rng.integers(0, 4))]
+        tf = int(rng.integers(0, 3))
+        if (kind == "r2c" and tf == 1) or (kind == "c2r" and tf == 2):
+            tf = 0
+        P = int(np.prod(mesh))
+        pid = int(rng.integers(0, P))
+        name = {"c2c": "dft", "r2c": "dft_r2c", "c2r": "dft_c2r", "r2r": "r2r"}[kind]
+        want = ref.local_block(name, n, n, mesh, pid, tf)
+        got = po.local_block(kind, n, n, mesh, pid, tf)
+        assert tuple(map(list, want)) == tuple(map(list, got))
+
+
+def test_transform_oracle_against_dft_definition():
+    """pocketfft restatement vs the O(n^2) definition (forward values are not pinned
+    by any reference test; the DFT definition is the anchor)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((5, 7, 6)) + 1j * rng.standard_normal((5, 7, 6))
+    for sign in (po.FORWARD, po.BACKWARD):
+        a = po.global_transform(po.C2C, x, [5, 7, 6], sign=sign)
+        b = po.brute_force_dft(x, sign)
+        assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-13
+    xr = rng.standard_normal((4, 5, 9))
+    a = po.global_transform(po.R2C, xr, [4, 5, 9])
+    b = po.brute_force_dft(xr, po.FORWARD)[:, :, :5]
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-13
+    back = po.global_transform(po.C2R, a, [4, 5, 9], sign=po.BACKWARD)
+    assert np.allclose(back, xr * xr.size, atol=1e-10)
+
+
+def test_survey_numpy_forward_values():
+    # SURVEY.md 8c (derived by the restated oracle): forward of the a11 pattern at 29x27x31
+    n = [29, 27, 31]
+    x = po.init_input("complex", n, n, [0, 0, 0])
+    X = po.global_transform(po.C2C, x, n)
+    assert abs(X[0, 0, 0] - (6687.614919969376 + 6131.20324008727j)) < 1e-8
+    assert abs(X[1, 2, 3] - (2198.945614340035 + 739.7122735812995j)) < 1e-8
+    assert abs(np.linalg.norm(X) - 3.288979778416490e+05) < 1e-6
+
+
+def test_pruned_and_roundtrip():
+    rng = np.random.default_rng(5)
+    ni, n, no = [4, 6, 5], [8, 9, 7], [8, 9, 7]
+    x = rng.standard_normal(ni) + 1j * rng.standard_normal(ni)
+    X = po.global_transform(po.C2C, x, n, ni=ni, no=no)
+    xp = np.zeros(n, complex)
+    xp[:4, :6, :5] = x
+    assert np.allclose(X, np.fft.fftn(xp))
+    back = po.global_transform(po.C2C, X, n, ni=no, no=ni, sign=po.BACKWARD)
+    assert np.allclose(back, x * np.prod(n))
+
+
+def test_shifted_semantics():
+    """SHIFTED_IN|SHIFTED_OUT means: user index g in [-n/2, n/2) on both sides,
+    Y[k] = sum_j X[j] exp(-2 pi i j k / n) with j,k centred (doc/features.tex)."""
+    n = [8, 6, 4]
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    Y = po.global_transform(po.C2C, x, n, flags=po.SHIFTED_IN | po.SHIFTED_OUT)
+    want = np.fft.fftshift(np.fft.fftn(np.fft.ifftshift(x)))
+    assert np.allclose(Y, want)
