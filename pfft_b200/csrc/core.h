@@ -1,0 +1,148 @@
+// core.h -- host-side data model of pfft_b200: problem description, block
+// decomposition, and the stage list ("schedule") a plan executes.  Pure integer
+// code; no MPI, no CUDA.  The same planner serves a real rank and a "virtual" rank
+// (tests enumerate every rank of a mesh in one process and simulate the schedule).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+namespace pfb {
+
+using INT = ptrdiff_t;
+constexpr int kMaxDims = 8;    // rnk_n
+constexpr int kMaxMesh = 3;    // rnk_pm
+constexpr int kMaxBatch = 4;   // batch dims a stage kernel indexes (after merging)
+constexpr int kMaxSeg = 32;    // ranks along one mesh dimension
+
+// public flag bits (include/pfft.h; reference api/pfft.h:528-545)
+enum : unsigned {
+  F_TRANSPOSED_IN = 1u << 0, F_TRANSPOSED_OUT = 1u << 1, F_SHIFTED_IN = 1u << 2, F_SHIFTED_OUT = 1u << 3,
+  F_PRESERVE_INPUT = 1u << 8, F_DESTROY_INPUT = 1u << 9, F_PADDED_R2C = 1u << 11
+};
+
+enum class Kind : int { C2C = 0, R2C = 1, C2R = 2, R2R = 3 };
+
+// ---- 1-D block decomposition (reference kernel/block.c:54-95) ----------------------
+INT block_count(INT n, INT blk);
+INT block_default(INT n, INT user_blk, int nprocs);   // user block or ceil(n/P)
+INT block_extent(INT n, INT blk, int which);          // 0 beyond the last block
+INT block_offset(INT n, INT blk, int which);          // 0 (not n) beyond the last block
+
+struct Problem {
+  int rnk_n = 0;
+  INT n[kMaxDims] = {0}, ni[kMaxDims] = {0}, no[kMaxDims] = {0};
+  INT howmany = 1;
+  bool has_iblock = false, has_oblock = false;
+  INT iblock[kMaxDims] = {0}, oblock[kMaxDims] = {0};
+  int rnk_pm = 0;              // mesh rank as the user built it (1..3)
+  int np[kMaxMesh] = {1, 1, 1};
+  Kind kind = Kind::C2C;
+  int sign = -1;
+  int r2r_kinds[kMaxDims] = {0};
+  bool has_skip = false;
+  int skip[kMaxMesh + 1] = {0};
+  unsigned flags = 0;
+};
+
+// what pfft_local_block_* / pfft_local_size_* report (reference kernel/partrafo.c:99-315)
+struct LocalSizes {
+  INT lni[kMaxDims], lis[kMaxDims], lno[kMaxDims], los[kMaxDims];
+};
+
+// Effective 2-D mesh behind a 3-D mesh for 3-D data (reference kernel/procmesh.c:191-391)
+struct Mesh3dto2d {
+  bool active = false;
+  int q0 = 1, q1 = 1;
+};
+Mesh3dto2d mesh_3dto2d(const Problem &p);
+void mesh_coords(int rnk_pm, const int *np, int pid, int *coords);   // row-major, last fastest
+
+// returns false when the reference planner would return NULL (kernel/partrafo.c:337-373)
+bool problem_is_legal(const Problem &p, std::string *why);
+void local_block(const Problem &p, int pid, LocalSizes *out);
+// elements (complex for c2c/r2c/c2r, real for r2r) the caller must allocate per array
+INT alloc_local(const Problem &p, int pid);
+
+// ---- schedule ---------------------------------------------------------------------
+enum StageOp : int { OP_COPY = 0, OP_C2C = 1, OP_R2C = 2, OP_C2R = 3, OP_R2R = 4 };
+
+struct BatchDim {
+  INT extent, istride, ostride;
+  int dim;   // logical dimension id (for diagnostics; -1 = tuple)
+};
+
+// ±1 modulation fused into a stage (reference api/api-basic.c:1186-1285):
+// factor(idx) = (g < half) ? ((g odd) ? -1 : 1) * extra : 1  with g = idx + start
+struct SignMod {
+  int on = 0;
+  INT start = 0, half = 0;
+  int extra = 1;
+};
+
+// One pass over the local array: (optionally) transform along one dimension and
+// re-lay the data out for what follows (next local stage, an exchange, or the user).
+// Element units: `in_real`/`out_real` say whether strides count reals or complex numbers.
+struct Stage {
+  int op = OP_COPY;
+  int sign = -1;
+  int r2r_kind = 0;
+  int dim = -1;               // logical dimension transformed / re-laid out
+  INT n = 1;                  // logical transform length (embed target)
+  INT nin = 1, zin = 0;       // elements present on input along `dim`, and their offset inside the length-n line
+  INT nout = 1, zout = 0;     // outputs kept: logical indices [zout, zout+nout)
+  // input addressing along `dim`: j -> seg = j / iblk; seg*iseg_stride + (j - seg*iblk)*istride
+  INT istride = 1, iblk = 1, iseg_stride = 0;
+  // output addressing along `dim`: k -> seg = k / oblk; obase[seg] + (k - seg*oblk)*ostride
+  INT ostride = 1, oblk = 1;
+  int noseg = 1;
+  INT oseg_off[kMaxSeg] = {0};   // element offset of chunk `seg` inside the destination's receive area (peer-local)
+  INT oseg_cnt[kMaxSeg] = {0};   // elements of chunk `seg` (what an exchange moves)
+  int nbatch = 0;
+  BatchDim batch[kMaxBatch];
+  int tile_dim = -1;          // index into batch[]: lines of one tile differ along it
+  bool in_real = false, out_real = false;
+  bool conj_in = false, conj_out = false;
+  SignMod mod_in, mod_out;
+  // plumbing
+  int in_buf = 0, out_buf = 0;   // buffer ids, see BufId
+  int exchange = -1;          // index into Schedule::exchanges applied to this stage's output, or -1
+  INT in_elems = 0, out_elems = 0;   // footprint in elements (for buffer sizing / roofline bytes)
+};
+
+enum BufId : int { BUF_USER_IN = 0, BUF_USER_OUT = 1, BUF_A = 2, BUF_B = 3 };
+
+// All-to-all over one mesh dimension. Chunk `p` of the producing stage goes to member
+// `p` of that mesh dimension's communicator and lands at recv_off[me] elements inside
+// its receive buffer (uniform chunk size per receiver).
+struct Exchange {
+  int mesh_dim = 0;
+  int nparts = 1;
+  int me = 0;
+  INT send_cnt[kMaxSeg] = {0};    // elements I send to member p
+  INT recv_cnt = 0;               // elements of every chunk I receive
+  INT peer_recv_cnt[kMaxSeg] = {0};   // chunk size at member p (offset of my chunk there = me * that)
+  bool elem_real = false;
+};
+
+struct Schedule {
+  Problem prob;
+  int pid = 0;
+  int rnk_pm_eff = 0;           // mesh rank the schedule runs on (2 for a remapped 3-D mesh)
+  int np_eff[kMaxMesh] = {1, 1, 1};
+  int coords_eff[kMaxMesh] = {0, 0, 0};
+  LocalSizes ls;
+  std::vector<Stage> stages;
+  std::vector<Exchange> exchanges;
+  INT scratch_elems = 0;        // complex (or real for r2r) elements per scratch buffer
+  std::string error;            // non-empty: unsupported configuration
+};
+
+// Build the schedule of rank `pid`. Returns false (with sched->error) when the
+// configuration is legal for the reference but not yet supported here.
+bool build_schedule(const Problem &p, int pid, Schedule *sched);
+std::string schedule_to_json(const Schedule &s);
+
+}  // namespace pfb

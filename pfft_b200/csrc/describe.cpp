@@ -1,0 +1,85 @@
+// describe.cpp -- MPI-free, CUDA-free entry points over the integer layer and the planner
+// (include/pfft_b200.h): used by tests to enumerate every rank of a mesh in one process.
+#include <string.h>
+
+#include <string>
+
+#include "core.h"
+#include "pfft_b200.h"
+
+namespace pfb {
+std::string &last_error_ref() {
+  static thread_local std::string e;
+  return e;
+}
+
+void fill_problem(Problem *p, int kind, int rnk_n, const INT *n, const INT *ni, const INT *no, INT howmany,
+                  const INT *iblock, const INT *oblock, int rnk_pm, const int *np, int sign, const int *kinds,
+                  const int *skip, unsigned flags) {
+  p->rnk_n = rnk_n;
+  for (int t = 0; t < rnk_n && t < kMaxDims; t++) {
+    p->n[t] = n ? n[t] : (ni ? ni[t] : 0);
+    p->ni[t] = ni ? ni[t] : p->n[t];
+    p->no[t] = no ? no[t] : p->n[t];
+    if (kinds) p->r2r_kinds[t] = kinds[t];
+  }
+  p->howmany = howmany;
+  p->rnk_pm = rnk_pm;
+  for (int t = 0; t < rnk_pm && t < kMaxMesh; t++) p->np[t] = np[t];
+  p->has_iblock = iblock != nullptr;
+  p->has_oblock = oblock != nullptr;
+  for (int t = 0; t < rnk_pm && t < kMaxMesh; t++) {
+    if (iblock) p->iblock[t] = iblock[t];
+    if (oblock) p->oblock[t] = oblock[t];
+  }
+  p->kind = (Kind)kind;
+  p->sign = sign;
+  p->has_skip = skip != nullptr;
+  if (skip)
+    for (int t = 0; t <= rnk_pm && t <= kMaxMesh; t++) p->skip[t] = skip[t];
+  p->flags = flags;
+}
+}  // namespace pfb
+
+using namespace pfb;
+
+extern "C" {
+
+const char *pfftb200_version(void) { return "pfft_b200 0.1 (sm_100a)"; }
+
+const char *pfftb200_last_error(void) { return last_error_ref().c_str(); }
+
+size_t pfftb200_describe_schedule(int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                                  ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                                  const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                                  unsigned pfft_flags, char *buf, size_t buflen) {
+  Problem p;
+  fill_problem(&p, kind, rnk_n, n, ni, no, howmany, iblock, oblock, rnk_pm, np, sign, kinds, skip_trafos, pfft_flags);
+  Schedule s;
+  build_schedule(p, pid, &s);
+  std::string j = schedule_to_json(s);
+  if (buf && buflen) {
+    size_t k = j.size() < buflen - 1 ? j.size() : buflen - 1;
+    memcpy(buf, j.data(), k);
+    buf[k] = 0;
+  }
+  return j.size() + 1;
+}
+
+void pfftb200_local_block(int kind, int rnk_n, const ptrdiff_t *ni, const ptrdiff_t *no, const ptrdiff_t *iblock,
+                          const ptrdiff_t *oblock, int rnk_pm, const int *np, int pid, unsigned pfft_flags,
+                          ptrdiff_t *local_ni, ptrdiff_t *local_i_start, ptrdiff_t *local_no,
+                          ptrdiff_t *local_o_start) {
+  Problem p;
+  fill_problem(&p, kind, rnk_n, ni, ni, no, 1, iblock, oblock, rnk_pm, np, -1, nullptr, nullptr, pfft_flags);
+  LocalSizes ls;
+  local_block(p, pid, &ls);
+  for (int t = 0; t < rnk_n; t++) {
+    local_ni[t] = ls.lni[t];
+    local_i_start[t] = ls.lis[t];
+    local_no[t] = ls.lno[t];
+    local_o_start[t] = ls.los[t];
+  }
+}
+
+}  // extern "C"

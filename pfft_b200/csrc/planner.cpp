@@ -1,0 +1,605 @@
+// planner.cpp -- turns a Problem into the stage list one rank executes.
+//
+// What is contractual (and therefore follows the reference): the user-visible
+// input and output layouts and the order in which dimensions are transformed,
+// embedded (ni -> n, just before that dimension's transform) and truncated
+// (n -> no, just after), reference kernel/partrafo-transposed.c:185-291,
+// kernel/outrafo.c:68-91,118-168, kernel/ousample.c:208-339, and which mesh
+// dimension exchanges which pair of array dimensions, kernel/transpose.c:87-112.
+// What is NOT contractual: every intermediate layout.  The reference's are dictated
+// by FFTW's transpose interface; here each stage writes the layout its successor
+// wants: a stage that precedes an exchange stores its output directly as
+// per-destination chunks (split dimension outermost, the dimension about to be
+// gathered innermost), and the stage after the exchange reads its lines straight
+// out of the received chunks.  No stand-alone pack / unpack / transpose pass exists.
+#include <stdio.h>
+
+#include <algorithm>
+#include <sstream>
+
+#include "core.h"
+
+namespace pfb {
+namespace {
+
+constexpr int kTuple = kMaxDims;   // pseudo dimension id of the howmany-tuple
+
+struct Layout {
+  int order[kMaxDims + 1];   // dim ids outer -> inner, tuple last
+  int nord = 0;
+  INT ext[kMaxDims + 1] = {0};
+  INT pitch[kMaxDims + 1] = {0};
+  INT stride[kMaxDims + 1] = {0};
+  INT total = 0;             // elements of the array (or of one received chunk)
+  int seg_dim = -1;          // dimension delivered in chunks by an exchange
+  INT seg_blk = 0, seg_stride = 0;
+  bool real = false;
+
+  void finish() {
+    INT s = 1;
+    for (int k = nord - 1; k >= 0; k--) {
+      stride[order[k]] = s;
+      s *= pitch[order[k]];
+    }
+    total = s;
+  }
+};
+
+struct HalfSizes {        // sizes one half of the schedule works with (physical units on complex sides)
+  bool active = false;
+  bool trafo = false;     // false: pure re-distribution (all stages copy)
+  Kind kind = Kind::C2C;
+  INT ni[kMaxDims], n[kMaxDims], no[kMaxDims];
+};
+
+struct Step {
+  int dim;
+  bool trafo;             // belongs to the transforming half
+  int half;               // 0 = forward ("transposed out"), 1 = backward ("transposed in")
+  int xch_mesh = -1;      // exchange after this step over this mesh dim
+  int xch_split = -1, xch_gather = -1;
+  INT split_blk = 0, split_n = 0, gather_blk = 0, gather_n = 0;
+};
+
+struct Builder {
+  const Problem &p;
+  Schedule &s;
+  int d, r;
+  int np[kMaxMesh], c[kMaxMesh];
+  unsigned tr;
+  INT iblk[kMaxMesh], mblk[kMaxMesh], oblk[kMaxMesh];
+  HalfSizes hs[2];
+  INT cur_ext[kMaxDims + 1];   // current local extents (complex-physical / real as stored)
+
+  Builder(const Problem &pp, Schedule &ss) : p(pp), s(ss) {}
+
+  INT phys(Kind k, const INT *n, int t) const {
+    return (t == d - 1 && (k == Kind::R2C || k == Kind::C2R)) ? n[t] / 2 + 1 : n[t];
+  }
+
+  bool setup() {
+    d = p.rnk_n;
+    r = p.rnk_pm;
+    tr = p.flags & (F_TRANSPOSED_IN | F_TRANSPOSED_OUT);
+    if (mesh_3dto2d(p).active) {
+      s.error = "3-D data on a 3-D process mesh (3dto2d remap) is not supported yet";
+      return false;
+    }
+    if (d > kMaxDims - 1 || r > kMaxMesh) {
+      s.error = "too many dimensions";
+      return false;
+    }
+    mesh_coords(r, p.np, s.pid, c);
+    for (int t = 0; t < r; t++) {
+      np[t] = p.np[t];
+      if (np[t] > kMaxSeg) {
+        s.error = "mesh dimension larger than 32";
+        return false;
+      }
+    }
+    s.rnk_pm_eff = r;
+    for (int t = 0; t < r; t++) {
+      s.np_eff[t] = np[t];
+      s.coords_eff[t] = c[t];
+    }
+    // blocks, reference kernel/partrafo.c:652-701
+    INT pni[kMaxDims], pno[kMaxDims];
+    for (int t = 0; t < d; t++) {
+      pni[t] = phys(p.kind, p.ni, t);
+      pno[t] = phys(p.kind, p.no, t);
+    }
+    const INT *pnm = (p.kind == Kind::C2R || (tr & F_TRANSPOSED_IN)) ? pni : pno;
+    const INT *mu = nullptr;
+    if (tr & F_TRANSPOSED_IN) mu = p.has_iblock ? p.iblock : nullptr;
+    if (tr & F_TRANSPOSED_OUT) mu = p.has_oblock ? p.oblock : nullptr;
+    for (int t = 0; t < r; t++) {
+      iblk[t] = block_default(pni[t], p.has_iblock && !(tr & F_TRANSPOSED_IN) ? p.iblock[t] : 0, np[t]);
+      mblk[t] = block_default(pnm[t + 1], mu ? mu[t] : 0, np[t]);
+      oblk[t] = block_default(pno[t], p.has_oblock && !(tr & F_TRANSPOSED_OUT) ? p.oblock[t] : 0, np[t]);
+    }
+    // the two halves, reference kernel/partrafo.c:735-834
+    HalfSizes &to = hs[0], &ti = hs[1];
+    to.active = !(tr & F_TRANSPOSED_IN);
+    ti.active = !(tr & F_TRANSPOSED_OUT);
+    to.kind = ti.kind = p.kind;
+    for (int t = 0; t < d; t++) {
+      to.ni[t] = p.ni[t]; to.n[t] = p.n[t]; to.no[t] = p.no[t];
+      ti.ni[t] = ti.n[t] = ti.no[t] = p.no[t];
+    }
+    to.trafo = true;
+    ti.trafo = false;
+    if (tr & F_TRANSPOSED_IN) {
+      ti.trafo = true;
+      for (int t = 0; t < d; t++) { ti.ni[t] = p.ni[t]; ti.n[t] = p.n[t]; ti.no[t] = p.no[t]; }
+    }
+    if (p.kind == Kind::R2C) {
+      ti.kind = Kind::C2C;
+      ti.ni[d - 1] = ti.n[d - 1] = ti.no[d - 1] = p.no[d - 1] / 2 + 1;
+    }
+    if (p.kind == Kind::C2R) {
+      to.trafo = false;
+      to.kind = Kind::C2C;
+      for (int t = 0; t < d; t++) to.ni[t] = to.n[t] = to.no[t] = p.ni[t];
+      to.ni[d - 1] = to.n[d - 1] = to.no[d - 1] = p.ni[d - 1] / 2 + 1;
+      ti.trafo = true;
+      for (int t = 0; t < d; t++) { ti.ni[t] = p.ni[t]; ti.n[t] = p.n[t]; ti.no[t] = p.no[t]; }
+    }
+    return true;
+  }
+
+  bool user_skip(int dim) const { return p.has_skip && p.skip[std::min(dim, p.rnk_pm)] != 0; }
+
+  bool mesh_trivial() const {
+    for (int t = 0; t < r; t++)
+      if (np[t] > 1) return false;
+    return true;
+  }
+
+  // ---- user layouts -------------------------------------------------------------
+  Layout user_layout(bool is_input) const {
+    const bool transposed = is_input ? (tr & F_TRANSPOSED_IN) : (tr & F_TRANSPOSED_OUT);
+    const INT *ln = is_input ? s.ls.lni : s.ls.lno;
+    Layout L;
+    int k = 0;
+    if (transposed) {
+      for (int t = 1; t <= r; t++) L.order[k++] = t;
+      L.order[k++] = 0;
+      for (int t = r + 1; t < d; t++) L.order[k++] = t;
+    } else {
+      for (int t = 0; t < d; t++) L.order[k++] = t;
+    }
+    L.order[k++] = kTuple;
+    L.nord = k;
+    for (int t = 0; t < d; t++) L.ext[t] = L.pitch[t] = ln[t];
+    L.ext[kTuple] = L.pitch[kTuple] = p.howmany;
+    L.real = p.kind == Kind::R2R || (is_input && p.kind == Kind::R2C) || (!is_input && p.kind == Kind::C2R);
+    L.finish();
+    return L;
+  }
+
+  // ---- one stage ------------------------------------------------------------------
+  // Lin/Lout carry extents of every dimension; along `a` Lin.ext = elements present, Lout.ext = kept.
+  void emit(const Step &st, const Layout &Lin, const Layout &Lout, const HalfSizes &h, bool first, bool last,
+            int noseg, const INT *seg_rows) {
+    Stage g;
+    const int a = st.dim;
+    const bool do_trafo = st.trafo && !user_skip(a);
+    g.dim = a;
+    g.in_real = Lin.real;
+    g.out_real = Lout.real;
+    g.sign = p.sign;
+    if (p.kind == Kind::C2R) g.sign = +1;
+    if (p.kind == Kind::R2C) g.sign = -1;
+    const bool si = p.flags & F_SHIFTED_IN, so = p.flags & F_SHIFTED_OUT;
+    if (st.trafo) {
+      g.n = h.n[a];
+      const bool rlast = a == d - 1;
+      if (h.kind == Kind::R2C && rlast) {
+        g.op = OP_R2C;
+        g.nin = h.ni[a];
+        g.zin = si ? (h.n[a] - h.ni[a]) / 2 : 0;
+        const INT pn = h.n[a] / 2 + 1, pno = h.no[a] / 2 + 1;
+        g.nout = pno;
+        g.zout = pn - pno;   // reference kernel/ousample.c:262-272 keeps the upper end
+      } else if (h.kind == Kind::C2R && rlast) {
+        g.op = OP_C2R;
+        const INT pn = h.n[a] / 2 + 1, pni = h.ni[a] / 2 + 1;
+        g.nin = pni;
+        g.zin = pn - pni;    // reference kernel/ousample.c:292-301
+        g.nout = h.no[a];
+        g.zout = so ? (h.n[a] - h.no[a]) / 2 : 0;
+      } else {
+        g.op = h.kind == Kind::R2R ? OP_R2R : OP_C2C;
+        g.r2r_kind = p.r2r_kinds[a];
+        g.nin = h.ni[a];
+        g.zin = si ? (h.n[a] - h.ni[a]) / 2 : 0;
+        g.nout = h.no[a];
+        g.zout = so ? (h.n[a] - h.no[a]) / 2 : 0;
+      }
+      if (!do_trafo) {
+        if (g.op == OP_R2C || g.op == OP_C2R) s.error = "skipping the real-data dimension of r2c/c2r is not supported";
+        g.op = OP_COPY;
+      }
+      // index-shift modulations, reference api/api-basic.c:1186-1285 (skipped dims untouched)
+      if (do_trafo && so) {
+        g.mod_in.on = 1;
+        g.mod_in.start = si ? -(p.ni[a] / 2) : 0;
+        g.mod_in.half = p.ni[a] / 2;
+        g.mod_in.extra = (si && (p.n[a] / 2) % 2) ? -1 : 1;
+      }
+      if (do_trafo && si) {
+        g.mod_out.on = 1;
+        g.mod_out.start = so ? -(p.no[a] / 2) : 0;
+        g.mod_out.half = p.no[a] / 2;
+        g.mod_out.extra = 1;
+      }
+    } else {
+      g.op = OP_COPY;
+      g.n = g.nin = g.nout = Lin.ext[a];
+      g.zin = g.zout = 0;
+    }
+    if (first && p.kind == Kind::C2R && p.sign == -1) g.conj_in = true;    // reference kernel/partrafo.c:428-443
+    if (last && p.kind == Kind::R2C && p.sign == +1) g.conj_out = true;
+
+    if (Lin.seg_dim >= 0 && Lin.seg_dim != a) {
+      s.error = "internal: gathered dimension is not the one transformed next";
+      return;
+    }
+    // fft-dim addressing
+    g.istride = Lin.stride[a];
+    if (Lin.seg_dim == a) {
+      g.iblk = Lin.seg_blk;
+      g.iseg_stride = Lin.seg_stride;
+    } else {
+      g.iblk = std::max<INT>(g.nin, 1);
+      g.iseg_stride = 0;
+    }
+    g.ostride = Lout.stride[a];
+    if (noseg > 0) {
+      g.noseg = noseg;
+      g.oblk = st.split_blk;
+      INT off = 0;
+      for (int q = 0; q < noseg; q++) {
+        g.oseg_cnt[q] = seg_rows[q] * Lout.stride[a];
+        g.oseg_off[q] = off;
+        off += g.oseg_cnt[q];
+      }
+    } else {
+      g.noseg = 1;
+      g.oblk = std::max<INT>(g.nout, 1);
+      g.oseg_cnt[0] = Lout.total;
+    }
+    // batch dims: everything except `a`, merged where both layouts allow
+    std::vector<BatchDim> b;
+    INT lines = 1;
+    for (int k = 0; k < Lin.nord; k++) {
+      int t = Lin.order[k];
+      if (t == a) continue;
+      lines *= Lin.ext[t];
+      if (Lin.ext[t] == 1) continue;
+      b.push_back({Lin.ext[t], Lin.stride[t], Lout.stride[t], t == kTuple ? -1 : t});
+    }
+    bool merged = true;
+    while (merged) {
+      merged = false;
+      for (size_t x = 0; x < b.size() && !merged; x++)
+        for (size_t y = 0; y < b.size() && !merged; y++) {
+          if (x == y) continue;
+          if (b[x].istride == b[y].istride * b[y].extent && b[x].ostride == b[y].ostride * b[y].extent) {
+            b[y].extent *= b[x].extent;
+            b.erase(b.begin() + x);
+            merged = true;
+          }
+        }
+    }
+    std::sort(b.begin(), b.end(), [](const BatchDim &x, const BatchDim &y) { return x.istride > y.istride; });
+    if ((int)b.size() > kMaxBatch) {
+      s.error = "more than 4 independent batch dimensions in one stage";
+      return;
+    }
+    g.nbatch = (int)b.size();
+    for (int k = 0; k < g.nbatch; k++) g.batch[k] = b[k];
+    // tile dimension: lines of one tile are neighbours along it (coalescing on the strided side)
+    g.tile_dim = -1;
+    if (g.nbatch > 0) {
+      auto pick = [&](bool by_out) {
+        int best = 0;
+        for (int k = 1; k < g.nbatch; k++) {
+          INT sk = by_out ? g.batch[k].ostride : g.batch[k].istride;
+          INT sb = by_out ? g.batch[best].ostride : g.batch[best].istride;
+          if (sk < sb) best = k;
+        }
+        return best;
+      };
+      if (g.ostride != 1) g.tile_dim = pick(true);
+      else g.tile_dim = pick(false);
+    }
+    g.in_elems = lines * g.nin;
+    g.out_elems = lines * g.nout;
+    s.stages.push_back(g);
+  }
+
+  // intermediate layout in front of an exchange: split dim outermost, gathered dim
+  // innermost (before the always-local trailing dims and the tuple)
+  Layout chunk_layout(int split, int gather, INT gather_pitch, bool real) const {
+    Layout L;
+    int k = 0;
+    L.order[k++] = split;
+    for (int t = 0; t <= r; t++)
+      if (t != split && t != gather) L.order[k++] = t;
+    L.order[k++] = gather;
+    for (int t = r + 1; t < d; t++) L.order[k++] = t;
+    L.order[k++] = kTuple;
+    L.nord = k;
+    for (int t = 0; t < d; t++) L.ext[t] = L.pitch[t] = cur_ext[t];
+    L.ext[kTuple] = L.pitch[kTuple] = p.howmany;
+    L.pitch[gather] = gather_pitch;
+    L.real = real;
+    return L;
+  }
+
+  Layout dense_like(const Layout &src, bool real) const {
+    Layout L = src;
+    for (int t = 0; t < d; t++) L.ext[t] = L.pitch[t] = cur_ext[t];
+    L.seg_dim = -1;
+    L.real = real;
+    L.finish();
+    return L;
+  }
+
+  bool build() {
+    if (!setup()) return false;
+    local_block(p, s.pid, &s.ls);
+    const HalfSizes &to = hs[0], &ti = hs[1];
+
+    // ---- step list
+    std::vector<Step> steps;
+    const bool local_only = mesh_trivial() && tr == 0;
+    if (local_only) {
+      // every "exchange" is the identity: transform in place of the layout, no return trip
+      const HalfSizes &h = to.trafo ? to : ti;
+      const int half = to.trafo ? 0 : 1;
+      if (p.kind == Kind::C2R) for (int a = 0; a < d; a++) steps.push_back({a, true, half});
+      else for (int a = d - 1; a >= 0; a--) steps.push_back({a, true, half});
+      (void)h;
+    } else {
+      if (to.active) {
+        if (to.trafo) for (int a = d - 1; a > r; a--) steps.push_back({a, true, 0});
+        for (int a = r; a >= 0; a--) {
+          Step st{a, to.trafo, 0};
+          if (a >= 1) {
+            const int m = a - 1;
+            st.xch_mesh = m;
+            st.xch_split = a;
+            st.xch_gather = m;
+            st.split_blk = mblk[m];
+            st.split_n = phys(to.kind, to.no, a);
+            st.gather_blk = iblk[m];
+            st.gather_n = phys(to.kind, to.ni, m);
+          }
+          steps.push_back(st);
+        }
+      }
+      if (ti.active) {
+        for (int a = 0; a <= r; a++) {
+          Step st{a, ti.trafo, 1};
+          if (a < r) {
+            const int m = a;
+            st.xch_mesh = m;
+            st.xch_split = a;
+            st.xch_gather = a + 1;
+            st.split_blk = oblk[m];
+            st.split_n = phys(ti.kind, ti.no, a);
+            st.gather_blk = mblk[m];
+            st.gather_n = phys(ti.kind, ti.ni, a + 1);
+          }
+          if (a == 0 && to.active) {
+            // merge with the forward half's dim-0 step (the reference's PHANTOM stage, kernel/partrafo.c:828-833)
+            Step &prev = steps.back();
+            const bool was_trafo = prev.trafo;
+            prev.xch_mesh = st.xch_mesh; prev.xch_split = st.xch_split; prev.xch_gather = st.xch_gather;
+            prev.split_blk = st.split_blk; prev.split_n = st.split_n;
+            prev.gather_blk = st.gather_blk; prev.gather_n = st.gather_n;
+            if (!was_trafo && st.trafo) { prev.trafo = true; prev.half = 1; }
+            continue;
+          }
+          steps.push_back(st);
+        }
+        if (ti.trafo) for (int a = r + 1; a < d; a++) steps.push_back({a, true, 1});
+      }
+    }
+    if (steps.empty()) {
+      s.error = "empty schedule";
+      return false;
+    }
+
+    // ---- walk the steps, tracking the layout
+    Layout cur = user_layout(true);
+    for (int t = 0; t < d; t++) cur_ext[t] = cur.ext[t];
+    // extents in complex-physical units where the user counts reals
+    bool cur_real = cur.real;
+    const Layout Lfinal = user_layout(false);
+
+    for (size_t i = 0; i < steps.size(); i++) {
+      const Step &st = steps[i];
+      const HalfSizes &h = hs[st.half];
+      const int a = st.dim;
+      const bool first = i == 0, last = i + 1 == steps.size();
+      // extent of `a` on input / output of this step
+      Layout Lin = cur;
+      bool out_real = cur_real;
+      INT out_ext;
+      if (st.trafo) {
+        const bool rlast = a == d - 1;
+        if (h.kind == Kind::R2C && rlast) out_real = false;
+        if (h.kind == Kind::C2R && rlast) out_real = true;
+        if (h.kind == Kind::R2C && rlast) {
+          Lin.ext[a] = h.ni[a];                 // logical reals present in a row (pitch may be padded)
+          out_ext = h.no[a] / 2 + 1;
+        } else if (h.kind == Kind::C2R && rlast) {
+          out_ext = h.no[a];
+        } else {
+          out_ext = phys(h.kind, h.no, a);
+        }
+      } else {
+        out_ext = Lin.ext[a];
+      }
+      cur_ext[a] = out_ext;
+
+      Layout Lout;
+      int noseg = 0;
+      INT seg_rows[kMaxSeg] = {0};
+      if (last) {
+        Lout = Lfinal;
+        if (Lout.real != out_real) { s.error = "internal: element type mismatch at the last stage"; return false; }
+      } else if (st.xch_mesh >= 0) {
+        const int m = st.xch_mesh;
+        Lout = chunk_layout(st.xch_split, st.xch_gather, st.gather_blk, out_real);
+        Lout.finish();
+        noseg = np[m];
+        for (int q = 0; q < noseg; q++) seg_rows[q] = block_extent(st.split_n, st.split_blk, q);
+        if (out_ext != st.split_n) { s.error = "internal: split extent mismatch"; return false; }
+      } else {
+        Lout = dense_like(Lin, out_real);
+        // keep the input's memory order; a C2R/R2C row changes element type, dense rows
+      }
+      if (last && out_ext != Lout.ext[a] && !(Lout.real && a == d - 1)) {
+        // the user's output block must hold exactly what the last stage keeps
+        s.error = "internal: output extent mismatch";
+        return false;
+      }
+      if (last && Lout.real && a == d - 1) {
+        // real rows may be padded (PFFT_PADDED_C2R): extent kept is `no`, pitch is the user's row length
+        Lout.ext[a] = out_ext;
+      }
+      emit(st, Lin, Lout, h, first, last, noseg, seg_rows);
+      if (!s.error.empty()) return false;
+      Stage &g = s.stages.back();
+
+      if (st.xch_mesh >= 0 && !last) {
+        const int m = st.xch_mesh;
+        Exchange x;
+        x.mesh_dim = m;
+        x.nparts = np[m];
+        x.me = c[m];
+        x.elem_real = out_real;
+        for (int q = 0; q < np[m]; q++) {
+          x.send_cnt[q] = g.oseg_cnt[q];
+          x.peer_recv_cnt[q] = g.oseg_cnt[q];
+        }
+        x.recv_cnt = g.oseg_cnt[c[m]];
+        g.exchange = (int)s.exchanges.size();
+        s.exchanges.push_back(x);
+        // layout the next stage reads: my rows of the split dim, the gathered dim whole (in chunks)
+        cur = Lout;
+        cur_ext[st.xch_split] = seg_rows[c[m]];
+        cur.ext[st.xch_split] = cur.pitch[st.xch_split] = seg_rows[c[m]];
+        cur.finish();
+        cur.seg_dim = st.xch_gather;
+        cur.seg_blk = st.gather_blk;
+        cur.seg_stride = cur.total;
+        cur.ext[st.xch_gather] = st.gather_n;
+        cur_ext[st.xch_gather] = st.gather_n;
+      } else {
+        cur = Lout;
+        cur.seg_dim = -1;
+      }
+      cur_real = out_real;
+    }
+
+    // buffers: in -> A -> B -> A ... -> out
+    INT scratch = 0;
+    for (size_t i = 0; i < s.stages.size(); i++) {
+      Stage &g = s.stages[i];
+      g.in_buf = i == 0 ? BUF_USER_IN : s.stages[i - 1].out_buf;
+      g.out_buf = i + 1 == s.stages.size() ? BUF_USER_OUT : (i % 2 == 0 ? BUF_A : BUF_B);
+      if (i + 1 < s.stages.size()) {
+        INT sendside = 0, recvside = 0;
+        for (int q = 0; q < g.noseg; q++) sendside += g.oseg_cnt[q];
+        if (g.exchange >= 0) {
+          const Exchange &x = s.exchanges[g.exchange];
+          recvside = x.recv_cnt * x.nparts;
+        }
+        const INT scal = g.out_real ? 1 : 2;
+        scratch = std::max(scratch, std::max(sendside, recvside) * scal);
+      }
+    }
+    s.scratch_elems = scratch;
+    return true;
+  }
+};
+
+}  // namespace
+
+bool build_schedule(const Problem &p, int pid, Schedule *sched) {
+  sched->prob = p;
+  sched->pid = pid;
+  sched->stages.clear();
+  sched->exchanges.clear();
+  sched->error.clear();
+  std::string why;
+  if (!problem_is_legal(p, &why)) {
+    sched->error = "illegal: " + why;
+    return false;
+  }
+  Builder b(p, *sched);
+  if (!b.build()) {
+    if (sched->error.empty()) sched->error = "unsupported configuration";
+    return false;
+  }
+  return sched->error.empty();
+}
+
+std::string schedule_to_json(const Schedule &s) {
+  std::ostringstream o;
+  auto arr = [&](const INT *v, int n) {
+    o << "[";
+    for (int i = 0; i < n; i++) o << (i ? "," : "") << v[i];
+    o << "]";
+  };
+  const int d = s.prob.rnk_n;
+  o << "{\"pid\":" << s.pid << ",\"rnk_n\":" << d << ",\"error\":\"" << s.error << "\"";
+  o << ",\"local_ni\":"; arr(s.ls.lni, d);
+  o << ",\"local_i_start\":"; arr(s.ls.lis, d);
+  o << ",\"local_no\":"; arr(s.ls.lno, d);
+  o << ",\"local_o_start\":"; arr(s.ls.los, d);
+  o << ",\"scratch_elems\":" << s.scratch_elems;
+  o << ",\"coords\":[";
+  for (int t = 0; t < s.rnk_pm_eff; t++) o << (t ? "," : "") << s.coords_eff[t];
+  o << "],\"np\":[";
+  for (int t = 0; t < s.rnk_pm_eff; t++) o << (t ? "," : "") << s.np_eff[t];
+  o << "],\"stages\":[";
+  for (size_t i = 0; i < s.stages.size(); i++) {
+    const Stage &g = s.stages[i];
+    o << (i ? "," : "") << "{\"op\":" << g.op << ",\"sign\":" << g.sign << ",\"r2r_kind\":" << g.r2r_kind
+      << ",\"dim\":" << g.dim << ",\"n\":" << g.n << ",\"nin\":" << g.nin << ",\"zin\":" << g.zin
+      << ",\"nout\":" << g.nout << ",\"zout\":" << g.zout << ",\"istride\":" << g.istride
+      << ",\"iblk\":" << g.iblk << ",\"iseg_stride\":" << g.iseg_stride << ",\"ostride\":" << g.ostride
+      << ",\"oblk\":" << g.oblk << ",\"noseg\":" << g.noseg << ",\"oseg_off\":";
+    arr(g.oseg_off, g.noseg);
+    o << ",\"oseg_cnt\":";
+    arr(g.oseg_cnt, g.noseg);
+    o << ",\"batch\":[";
+    for (int k = 0; k < g.nbatch; k++)
+      o << (k ? "," : "") << "[" << g.batch[k].extent << "," << g.batch[k].istride << "," << g.batch[k].ostride
+        << "," << g.batch[k].dim << "]";
+    o << "],\"tile_dim\":" << g.tile_dim << ",\"in_real\":" << (int)g.in_real << ",\"out_real\":" << (int)g.out_real
+      << ",\"conj_in\":" << (int)g.conj_in << ",\"conj_out\":" << (int)g.conj_out << ",\"mod_in\":[" << g.mod_in.on
+      << "," << g.mod_in.start << "," << g.mod_in.half << "," << g.mod_in.extra << "],\"mod_out\":[" << g.mod_out.on
+      << "," << g.mod_out.start << "," << g.mod_out.half << "," << g.mod_out.extra << "],\"in_buf\":" << g.in_buf
+      << ",\"out_buf\":" << g.out_buf << ",\"exchange\":" << g.exchange << ",\"in_elems\":" << g.in_elems
+      << ",\"out_elems\":" << g.out_elems << "}";
+  }
+  o << "],\"exchanges\":[";
+  for (size_t i = 0; i < s.exchanges.size(); i++) {
+    const Exchange &x = s.exchanges[i];
+    o << (i ? "," : "") << "{\"mesh_dim\":" << x.mesh_dim << ",\"nparts\":" << x.nparts << ",\"me\":" << x.me
+      << ",\"recv_cnt\":" << x.recv_cnt << ",\"elem_real\":" << (int)x.elem_real << ",\"send_cnt\":";
+    arr(x.send_cnt, x.nparts);
+    o << "}";
+  }
+  o << "]}";
+  return o.str();
+}
+
+}  // namespace pfb
