@@ -1,0 +1,75 @@
+// fft_tables.cpp -- host-side tables for the FFT kernels: radix factorisation and
+// twiddle factors.  Twiddles are evaluated in long double after reducing the angle
+// to the first octant, so every fp64 entry is correctly rounded to well below 1 ulp;
+// the kernels never call sincos (fp64 accuracy target: 1e-12 relative L2 over a
+// 1024^3 transform, BASELINE.json north_star).
+#include <math.h>
+
+#include "kernels.h"
+
+namespace pfb {
+
+int factorize_generic(int L, int *fac) {
+  int nf = 0;
+  int m = L;
+  while (m % 4 == 0) { fac[nf++] = 4; m /= 4; }
+  for (int p = 2; p <= 7 && m > 1; p++)
+    while (m % p == 0) { fac[nf++] = p; m /= p; }
+  for (int p = 11; (long long)p * p <= m; p += 2)
+    while (m % p == 0) { fac[nf++] = p; m /= p; }
+  if (m > 1) fac[nf++] = m;
+  if (nf == 0) fac[nf++] = 1;
+  return nf;
+}
+
+// exp(-2*pi*i*k/L) with the angle folded into [0, pi/4]
+static void unit_root(long long k, long long L, long double *c, long double *s) {
+  const long double two_pi = 6.283185307179586476925286766559005768L;
+  k %= L;
+  if (k < 0) k += L;
+  // work in eighths of a turn: position = 8k/L
+  long long k8 = 8 * k;
+  int oct = (int)(k8 / L);                 // 0..7
+  long long rem8 = k8 - (long long)oct * L;   // 0 <= rem8 < L, angle within octant = rem8/(8L) turns
+  long double a;
+  bool flip = oct & 1;                      // odd octant: measure from the octant's upper edge
+  if (flip) a = two_pi * (long double)(L - rem8) / (8.0L * (long double)L);
+  else a = two_pi * (long double)rem8 / (8.0L * (long double)L);
+  long double ca = cosl(a), sa = sinl(a);
+  if (flip) { long double t = ca; ca = sa; sa = t; }   // angle within quadrant = pi/2 - a'
+  // now (ca, sa) = (cos, sin) of the angle within the quadrant q = oct/2
+  long double cq, sq;
+  switch (oct / 2) {
+    case 0: cq = ca; sq = sa; break;
+    case 1: cq = -sa; sq = ca; break;
+    case 2: cq = -ca; sq = -sa; break;
+    default: cq = sa; sq = -ca; break;
+  }
+  *c = cq;
+  *s = -sq;   // forward sign: exp(-i theta)
+}
+
+void make_twiddles_f64(int L, double *re_im) {
+  for (int k = 0; k < L; k++) {
+    long double c, s;
+    unit_root(k, L, &c, &s);
+    re_im[2 * k] = (double)c;
+    re_im[2 * k + 1] = (double)s;
+  }
+}
+
+void make_twiddles_f32(int L, float *re_im) {
+  for (int k = 0; k < L; k++) {
+    long double c, s;
+    unit_root(k, L, &c, &s);
+    re_im[2 * k] = (float)c;
+    re_im[2 * k + 1] = (float)s;
+  }
+}
+
+unsigned long long &launch_counter() {
+  static unsigned long long n = 0;
+  return n;
+}
+
+}  // namespace pfb

@@ -1,0 +1,62 @@
+// kernels.h -- device-side contract of one schedule stage (see core.h: Stage).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "core.h"
+
+namespace pfb {
+
+constexpr int kMaxFactors = 24;
+
+struct SignModDev {
+  int on, start, half, extra;
+};
+
+// Plain-old-data copy of a Stage plus pointers; passed to kernels by value.
+struct StageParams {
+  const void *in;
+  void *out[kMaxSeg];        // base pointer of output chunk `seg`
+  int op, sign, r2r_kind;
+  int n;                     // logical transform length
+  int L;                     // complex FFT length executed on a line
+  int nin, zin, nout, zout;
+  long long istride, iseg_stride;
+  int iblk;
+  long long ostride;
+  int oblk, noseg;
+  int nbatch;
+  long long bext[kMaxBatch], bis[kMaxBatch], bos[kMaxBatch];
+  int tile_dim;              // -1: single line
+  int tl;                    // lines per tile
+  long long tiles_along;     // tiles along tile_dim
+  long long ntiles;
+  int in_real, out_real, conj_in, conj_out;
+  SignModDev mod_in, mod_out;
+  const void *twiddle;       // L entries exp(-2*pi*i*k/L) in the stage's precision
+  int nfac;
+  int fac[kMaxFactors];
+};
+
+// host-side helpers (fft_tables.cpp)
+int factorize_generic(int L, int *fac);          // radices for the generic shared-memory kernel
+void make_twiddles_f64(int L, double *re_im);    // 2*L doubles, accurate to < 1 ulp
+void make_twiddles_f32(int L, float *re_im);
+
+// generic (any length) stage kernel; returns cudaErrorInvalidValue if the line does not fit
+template <typename T>
+cudaError_t launch_stage_generic(StageParams &sp, cudaStream_t stream);
+template <typename T>
+int generic_pick_tile(const Stage &g, int L);    // lines per tile (0: does not fit in shared memory)
+
+// fast path: power-of-two complex lines held in registers (fft_pow2.cu)
+template <typename T>
+bool pow2_supported(const Stage &g, int L);
+template <typename T>
+cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream);
+template <typename T>
+int pow2_pick_tile(const Stage &g, int L);
+
+unsigned long long &launch_counter();
+
+}  // namespace pfb

@@ -1,0 +1,187 @@
+"""GPU parity tests (-m gpu): the CUDA path behind the C ABI against the oracle.
+
+fp64 bar: relative max error <= 1e-12 (north_star: rel. L2 <= 1e-12); fp32: <= 1e-5.
+Small sizes go through the numpy oracle on the gathered array; the reference's own
+round-trip check (pfft_init_input_* -> forward -> clear -> backward -> scale ->
+pfft_check_output_*, tests/simple_check_c2c.c:17-69, tol 1e-12 in tests/run_checks.sh:75)
+is run at small and at BASELINE sizes."""
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import pfft_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+T_IN, T_OUT, PAD = po.TRANSPOSED_IN, po.TRANSPOSED_OUT, po.PADDED_R2C
+S_IN, S_OUT = po.SHIFTED_IN, po.SHIFTED_OUT
+TOL = {"double": 1e-12, "single": 2e-5}
+
+
+@pytest.fixture(scope="module")
+def world(built_lib):
+    import pfft_b200 as pf
+    pf.init()
+    return pf
+
+
+def _id(c):
+    return "%s-%s-np%s-f%d-%s%s" % (c["kind"], "x".join(map(str, c["n"])), "x".join(map(str, c["np"])),
+                                    c.get("flags", 0), c.get("precision", "double")[0], c.get("tag", ""))
+
+
+SINGLE_RANK = [
+    dict(kind="c2c", n=[8, 8, 8], np=[1, 1]),
+    dict(kind="c2c", n=[8, 8, 8], np=[1, 1], sign=+1),
+    dict(kind="c2c", n=[29, 27, 31], np=[1, 1]),                 # the reference test's odd sizes
+    dict(kind="c2c", n=[29, 27, 31], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[29, 27, 31], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[64, 32, 128], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[64, 32, 128], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[64, 64, 64], np=[1]),
+    dict(kind="c2c", n=[128, 16, 256], np=[1, 1]),
+    dict(kind="c2c", n=[16, 8, 1024], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[1024, 8, 16], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[12, 10, 18, 6], np=[1, 1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[16, 16, 16, 16], np=[1, 1, 1]),
+    dict(kind="c2c", n=[32, 20], np=[1]),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], howmany=3),
+    dict(kind="c2c", n=[64, 32, 16], np=[1, 1], precision="single"),
+    dict(kind="c2c", n=[29, 27, 31], np=[1, 1], precision="single", flags=T_OUT),
+    dict(kind="c2c", n=[16, 16, 16], np=[1, 1], memory="host"),
+    dict(kind="c2c", n=[16, 16, 16], np=[1, 1], inplace=True),
+    dict(kind="c2c", n=[16, 16, 16], np=[1, 1], inplace=True, flags=T_OUT),
+    dict(kind="r2c", n=[16, 12, 10], np=[1, 1]),
+    dict(kind="r2c", n=[29, 27, 31], np=[1, 1], flags=T_OUT),
+    dict(kind="r2c", n=[32, 16, 64], np=[1, 1], flags=T_OUT | PAD),
+    dict(kind="r2c", n=[16, 12, 10], np=[1, 1], sign=+1),
+    dict(kind="c2r", n=[16, 12, 10], np=[1, 1], sign=+1),
+    dict(kind="c2r", n=[29, 27, 31], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2r", n=[32, 16, 64], np=[1, 1], flags=T_IN | PAD, sign=+1),
+    dict(kind="c2r", n=[16, 12, 10], np=[1, 1], sign=-1),
+    dict(kind="r2c", n=[32, 16, 64], np=[1, 1], precision="single", flags=T_OUT | PAD),
+    dict(kind="c2c", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[1, 1]),
+    dict(kind="c2c", n=[12, 10, 9], ni=[12, 10, 9], no=[5, 7, 3], np=[1, 1], flags=T_OUT),
+    dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[1, 1], flags=T_OUT),
+    dict(kind="c2r", n=[29, 27, 31], ni=[29, 27, 31], no=[16, 16, 16], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=S_IN | S_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=S_IN | S_OUT | T_OUT),
+    dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[1, 1], flags=S_IN | S_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], skip=[0, 1, 0]),
+]
+
+
+@pytest.mark.parametrize("case", SINGLE_RANK, ids=_id)
+def test_single_rank_matches_oracle(world, case):
+    import gpu_worker
+    comm = world.create_procmesh(case["np"])
+    res = gpu_worker.run_case(case, comm)
+    comm.free()
+    assert res["error"] == "", res["error"]
+    err = gpu_worker.check_case(case, [res])
+    assert err < TOL[case.get("precision", "double")], err
+    assert res["input_preserved"], "out-of-place plans must not touch the input (PFFT_PRESERVE_INPUT default)"
+
+
+MULTI_RANK = [
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2]),                       # BASELINE configs[0]
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[64, 32, 128], np=[2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[16, 12, 10], np=[4]),
+    dict(kind="c2c", n=[13, 14, 19, 17], np=[2, 2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[5, 4, 3], np=[3, 2]),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="c2r", n=[29, 27, 31], np=[2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[32, 32, 32], np=[2, 2], flags=T_OUT, precision="single"),
+    dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[2, 2], flags=T_OUT),
+]
+
+
+def run_multi(case, timeout=300, env_extra=None):
+    import gpu_worker
+    P = int(np.prod(case["np"]))
+    with tempfile.TemporaryDirectory() as td:
+        json.dump(case, open(os.path.join(td, "case.json"), "w"))
+        env = dict(os.environ)
+        env.update(env_extra or {})
+        cmd = [os.path.join(ROOT, "pfft_b200", "bin", "pfftrun"), "-np", str(P), "-timeout", str(timeout),
+               sys.executable, os.path.join(ROOT, "tests", "gpu_worker.py"), os.path.join(td, "case.json"), td]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout + 30, env=env)
+        assert p.returncode == 0, (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+        results = []
+        for rk in range(P):
+            meta = json.load(open(os.path.join(td, "rank%d.json" % rk)))
+            assert meta.get("error", "") == "", meta["error"]
+            meta["out"] = np.load(os.path.join(td, "rank%d.npy" % rk))
+            results.append(meta)
+    return gpu_worker.check_case(case, results), results
+
+
+@pytest.mark.parametrize("case", MULTI_RANK, ids=_id)
+def test_multi_rank_on_one_gpu_matches_oracle(built_lib, case):
+    """N ranks share GPU 0; exchanges go through peer-mapped (CUDA IPC) stores."""
+    err, results = run_multi(case)
+    assert err < TOL[case.get("precision", "double")], err
+    assert all(r["transport"] == "p2p" for r in results)
+
+
+def _round_trip(world, n, np_, flags_f, flags_b, dtype=np.complex128, device_memory=False):
+    """The reference's own check (tests/simple_check_c2c.c): returns pfft_check_output's max error."""
+    pf = world
+    comm = pf.create_procmesh(np_)
+    alloc, lni, lis, lno, los = pf.local_size("c2c", n, comm, flags_f)
+    a = pf.alloc_complex(alloc, dtype)
+    b = pf.alloc_complex(alloc, dtype)
+    fwd = pf.plan_dft(n, a, b, comm, pf.FORWARD, flags_f | pf.DESTROY_INPUT, dtype=dtype)
+    bwd = pf.plan_dft(n, b, a, comm, pf.BACKWARD, flags_b | pf.DESTROY_INPUT, dtype=dtype)
+    assert fwd is not None and bwd is not None, pf.last_error()
+    pf.init_input("complex", n, lni, lis, a, dtype=dtype)
+    fwd.execute()
+    pf.clear_input("complex", n, lni, lis, a, dtype=dtype)
+    bwd.execute()
+    cnt = int(np.prod(lni))
+    a.array[:cnt] /= float(np.prod(n))
+    err = pf.check_output("complex", n, lni, lis, a, comm, dtype=dtype)
+    fwd.destroy(); bwd.destroy(); a.free(); b.free(); comm.free()
+    return err
+
+
+def test_reference_round_trip_small(world):
+    assert _round_trip(world, [29, 27, 31], [1, 1], 0, 0) < 1e-12
+    assert _round_trip(world, [29, 27, 31], [1, 1], T_OUT, T_IN) < 1e-12
+    assert _round_trip(world, [16, 16, 16], [1, 1], T_OUT, T_IN, dtype=np.complex64) < 1e-4
+
+
+def test_reference_round_trip_baseline_size(world):
+    """BASELINE configs[1] shape on one GPU: 512^3 c2c fp64, TRANSPOSED_OUT / TRANSPOSED_IN."""
+    err = _round_trip(world, [512, 512, 512], [1, 1], T_OUT, T_IN)
+    assert err < 1e-12, err
+
+
+def test_linearity_and_parseval_at_size(world):
+    """Size-independent properties at 256^3: Parseval and linearity of the forward transform."""
+    import torch
+    pf = world
+    n = [256, 256, 256]
+    comm = pf.create_procmesh([1, 1])
+    N = int(np.prod(n))
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(N, 2, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.randn(N, 2, dtype=torch.float64, device="cuda", generator=g)
+    X = torch.empty_like(x); Y = torch.empty_like(x); Z = torch.empty_like(x)
+    plan = pf.plan_dft(n, x, X, comm, pf.FORWARD, T_OUT)
+    plan.execute(x, X)
+    plan.execute(y, Y)
+    z = 2.0 * x - 3.0 * y
+    plan.execute(z, Z)
+    lin = (Z - (2.0 * X - 3.0 * Y)).norm() / Z.norm()
+    pars = abs((X.norm() ** 2 / N - x.norm() ** 2) / x.norm() ** 2)
+    plan.destroy(); comm.free()
+    assert lin.item() < 1e-13 and pars.item() < 1e-12

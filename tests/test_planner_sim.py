@@ -1,0 +1,112 @@
+"""CPU tests of the planner: every rank's stage list is interpreted in numpy
+(tests/schedule_sim.py) and the gathered result must equal the oracle's global
+transform.  This covers the N>1 host logic (chunking, exchanges, ragged and empty
+blocks) without a GPU."""
+import numpy as np
+import pytest
+
+import cases
+import pfft_b200 as pf
+import pfft_oracle as po
+import schedule_sim as ss
+
+T_IN, T_OUT, PAD = po.TRANSPOSED_IN, po.TRANSPOSED_OUT, po.PADDED_R2C
+S_IN, S_OUT = po.SHIFTED_IN, po.SHIFTED_OUT
+
+
+def run_virtual(case, seed=0):
+    np_ = case["np"]
+    P = int(np.prod(np_))
+    r = len(np_)
+    scheds = [pf.describe_schedule(case["kind"], case["n"], np_, pid, case.get("flags", 0), case.get("ni"),
+                                   case.get("no"), case.get("howmany", 1), case.get("iblock"), case.get("oblock"),
+                                   case.get("sign", -1), case.get("kinds"), case.get("skip")) for pid in range(P)]
+    for s in scheds:
+        assert s["error"] == "", s["error"]
+    xg = cases.make_global_input(case, seed)
+    user_in = [cases.local_input(case, xg, s["local_ni"], s["local_i_start"], r) for s in scheds]
+    outs = ss.simulate(scheds, user_in)
+    want = cases.oracle_output(case, xg)
+    scale = max(1e-300, float(np.abs(want).max()))
+    err = max(cases.compare_local_output(case, want, outs[pid], s["local_no"], s["local_o_start"], r)
+              for pid, s in enumerate(scheds))
+    return err / scale, scheds
+
+
+CASES = [
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2]),                       # BASELINE config 1
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1]),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[16, 12, 10], np=[4]),                          # slab
+    dict(kind="c2c", n=[16, 12, 10], np=[4], flags=T_OUT),
+    dict(kind="c2c", n=[16, 12, 10], np=[3], flags=T_IN),
+    dict(kind="c2c", n=[13, 14, 19, 17], np=[2, 2, 2], flags=T_OUT),   # 4-D on a 3-D mesh
+    dict(kind="c2c", n=[13, 14, 19, 17], np=[2, 2, 2]),
+    dict(kind="c2c", n=[13, 14, 19, 17], np=[2, 2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[13, 14, 19, 17], np=[3, 2], flags=T_OUT),
+    dict(kind="c2c", n=[5, 4, 3], np=[3, 2]),                          # ragged + empty ranks
+    dict(kind="c2c", n=[4, 4, 4], np=[3, 3], flags=T_OUT),
+    dict(kind="c2c", n=[6, 5], np=[2]),                                # 2-D on a 1-D mesh
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], howmany=3),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], howmany=2, flags=T_OUT),
+    dict(kind="c2c", n=[16, 12, 10], np=[2, 2], iblock=[9, 7], oblock=[10, 8]),
+    dict(kind="c2c", n=[16, 12, 10], np=[2, 2], oblock=[7, 6], flags=T_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], skip=[0, 1, 0]),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], skip=[1, 0, 1], flags=T_OUT),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2]),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="r2c", n=[16, 12, 10], np=[2, 2], flags=T_OUT | PAD),
+    dict(kind="r2c", n=[16, 12, 10], np=[2, 2], flags=T_OUT, sign=+1),
+    dict(kind="c2r", n=[29, 27, 31], np=[2, 2], sign=+1),
+    dict(kind="c2r", n=[29, 27, 30], np=[2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2r", n=[16, 12, 10], np=[2, 2], flags=T_IN | PAD, sign=+1),
+    dict(kind="c2r", n=[16, 12, 10], np=[2, 2], flags=T_IN, sign=-1),
+    dict(kind="r2c", n=[8, 6, 10], np=[1, 1]),
+    dict(kind="c2r", n=[8, 6, 10], np=[1, 1], sign=+1),
+    # pruned / oversampled (reference tests/simple_check_ousam_*.c use 16^3 -> 29x27x31)
+    dict(kind="c2c", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[2, 2]),
+    dict(kind="c2c", n=[12, 10, 9], ni=[12, 10, 9], no=[5, 7, 3], np=[2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[12, 10, 9], ni=[6, 5, 4], no=[5, 7, 3], np=[2, 2], flags=T_IN, sign=+1),
+    dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="c2r", n=[29, 27, 31], ni=[29, 27, 31], no=[16, 16, 16], np=[2, 2], flags=T_IN, sign=+1),
+    # index shifts
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_IN | S_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_IN | S_OUT | T_OUT),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_IN),
+    dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_OUT),
+    dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[2, 2], flags=S_IN | S_OUT),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "%s-%s-np%s-f%d" % (
+    c["kind"], "x".join(map(str, c["n"])), "x".join(map(str, c["np"])), c.get("flags", 0)))
+def test_schedule_reproduces_oracle(built_lib, case):
+    err, _ = run_virtual(case)
+    assert err < 1e-12, err
+
+
+def test_local_sizes_in_schedule_match_golden_values(built_lib):
+    s = pf.describe_schedule("c2c", [29, 27, 31], [2, 2], 3, T_OUT)
+    assert (s["local_ni"], s["local_i_start"], s["local_no"], s["local_o_start"]) == \
+        ([14, 13, 31], [15, 14, 0], [29, 13, 15], [0, 14, 16])
+
+
+def test_transposed_out_has_no_extra_passes(built_lib):
+    """One read + one write of the array per transformed dimension: 3 stages, 2 exchanges."""
+    s = pf.describe_schedule("c2c", [1024, 1024, 1024], [2, 4], 7, T_OUT)
+    assert len(s["stages"]) == 3 and len(s["exchanges"]) == 2
+    assert [g["dim"] for g in s["stages"]] == [2, 1, 0]
+    # headline config: every chunk of the first exchange is 512 MiB of complex doubles
+    assert s["exchanges"][0]["send_cnt"] == [512 * 256 * 256] * 4
+    assert s["exchanges"][1]["send_cnt"] == [512 * 256 * 512] * 2
+
+
+def test_illegal_combinations_are_refused(built_lib):
+    assert pf.describe_schedule("c2c", [8, 8, 8], [2, 2], 0, T_IN | T_OUT)["error"].startswith("illegal")
+    assert pf.describe_schedule("r2c", [8, 8, 8], [2, 2], 0, T_IN)["error"].startswith("illegal")
+    assert pf.describe_schedule("c2r", [8, 8, 8], [2, 2], 0, T_OUT)["error"].startswith("illegal")
+    assert pf.describe_schedule("c2c", [9, 8, 8], [2, 2], 0, S_IN)["error"].startswith("illegal")
+    assert pf.describe_schedule("c2c", [8, 8], [2, 2], 0, 0)["error"].startswith("illegal")
