@@ -1,13 +1,413 @@
-// fft_pow2.cu -- register-resident power-of-two stage kernel (placeholder: not enabled yet).
+// fft_pow2.cu -- register-resident power-of-two stage kernel for sm_100a (the hot
+// kernel of the headline benchmark: three of these per 1024^3 transform).
+//
+// One CTA owns a tile of `tl` lines.  A line of N complex points is spread over
+// N/E threads, E points per thread, in the "strided" distribution
+//     thread t holds indices  t, t + N/E, t + 2N/E, ...
+// which the Stockham autosort formulation preserves: every pass reads exactly
+// that set and the last pass leaves its outputs in it again.  Consequences:
+//   * the first pass loads straight from global memory into registers and the last
+//     pass stores straight from registers, both coalesced -- either along the line
+//     (thread index = line-major) or, for the strided/transposed side of a stage,
+//     along the tile (thread index = tile-minor, so a warp touches `tl` neighbouring
+//     lines = tl*16 contiguous bytes per point);
+//   * shared memory is used only for the exchanges between passes (2 for N = 1024),
+//     and the change between the load mapping and the store mapping of threads
+//     happens for free inside the last exchange: no separate transpose, pack or
+//     unpack pass ever touches HBM.
+// Zero padding (ni < n), truncation (no < n), chunked sources/destinations of the
+// exchanges, the +-1 index-shift modulation and conjugation are all applied in the
+// load / store of this one kernel.  Backward transforms swap re/im on load and store
+// around the same forward butterflies.
+//
+// Reference counterpart: FFTW guru64 plan + FFTW rank-0 copy plan per stage
+// (kernel/sertrafo.c:489-554,604-646), i.e. two passes over memory; here it is one.
+#include <cuda_runtime.h>
+
 #include "kernels.h"
+
 namespace pfb {
-template <typename T> bool pow2_supported(const Stage &, int) { return false; }
-template <typename T> int pow2_pick_tile(const Stage &, int) { return 0; }
-template <typename T> cudaError_t launch_stage_pow2(StageParams &, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace {
+
+template <typename T> struct C2 { using type = void; };
+template <> struct C2<double> { using type = double2; };
+template <> struct C2<float> { using type = float2; };
+
+template <typename T>
+struct alignas(2 * sizeof(T)) cx {
+  T x, y;
+};
+
+template <typename T>
+__device__ __forceinline__ cx<T> cmul(cx<T> a, cx<T> b) {
+  cx<T> r;
+  r.x = a.x * b.x - a.y * b.y;
+  r.y = a.x * b.y + a.y * b.x;
+  return r;
+}
+
+// ---- forward DFTs of length 2, 4, 8, 16 on registers ---------------------------------
+// dftR leaves output q in slot perm(q); slot_of<R>(q) gives that slot.
+template <typename T>
+__device__ __forceinline__ void dft2(cx<T> &a, cx<T> &b) {
+  cx<T> t = a;
+  a.x = t.x + b.x; a.y = t.y + b.y;
+  b.x = t.x - b.x; b.y = t.y - b.y;
+}
+
+// natural-order 4-point forward DFT: (a,b,c,d) -> (X0,X1,X2,X3)
+template <typename T>
+__device__ __forceinline__ void dft4(cx<T> &a, cx<T> &b, cx<T> &c, cx<T> &d) {
+  cx<T> s0{a.x + c.x, a.y + c.y}, s1{a.x - c.x, a.y - c.y};
+  cx<T> s2{b.x + d.x, b.y + d.y}, s3{b.x - d.x, b.y - d.y};
+  a.x = s0.x + s2.x; a.y = s0.y + s2.y;          // X0
+  c.x = s0.x - s2.x; c.y = s0.y - s2.y;          // X2
+  b.x = s1.x + s3.y; b.y = s1.y - s3.x;          // X1 = s1 - i*s3
+  d.x = s1.x - s3.y; d.y = s1.y + s3.x;          // X3 = s1 + i*s3
+}
+
+template <typename T, int R>
+struct Dft;
+
+template <typename T>
+struct Dft<T, 2> {
+  __device__ __forceinline__ static void run(cx<T> *v) { dft2(v[0], v[1]); }
+};
+template <typename T>
+struct Dft<T, 4> {
+  __device__ __forceinline__ static void run(cx<T> *v) { dft4(v[0], v[1], v[2], v[3]); }
+};
+template <typename T>
+struct Dft<T, 8> {
+  // r = 2*r1 + r0 (r0 in 0..1, r1 in 0..3), q = q0 + 4*q1 (q0 in 0..3, q1 in 0..1)
+  __device__ __forceinline__ static void run(cx<T> *v) {
+    // step 1: for each r0, 4-point DFT over r1 of v[2*r1 + r0]  -> slot r0 + 2*q0
+    dft4(v[0], v[2], v[4], v[6]);
+    dft4(v[1], v[3], v[5], v[7]);
+    // step 2: twiddle A_{r0=1}[q0] by w8^{q0}
+    const T h = (T)0.70710678118654752440;
+    { cx<T> t = v[3]; v[3].x = (t.x + t.y) * h; v[3].y = (t.y - t.x) * h; }     // w8^1 = (1 - i)/sqrt2
+    { cx<T> t = v[5]; v[5].x = t.y; v[5].y = -t.x; }                              // w8^2 = -i
+    { cx<T> t = v[7]; v[7].x = (t.y - t.x) * h; v[7].y = -(t.x + t.y) * h; }      // w8^3 = (-1 - i)/sqrt2
+    // step 3: for each q0, 2-point DFT over r0 of slots (2*q0, 2*q0+1) -> V[q0 + 4*q1] in slot 2*q0 + q1
+    dft2(v[0], v[1]);
+    dft2(v[2], v[3]);
+    dft2(v[4], v[5]);
+    dft2(v[6], v[7]);
+  }
+};
+template <typename T>
+struct Dft<T, 16> {
+  __device__ __forceinline__ static void run(cx<T> *v) {
+    // step 1: for each r0 in 0..3, DFT4 over r1 of v[4*r1 + r0] -> slot r0 + 4*q0
+    dft4(v[0], v[4], v[8], v[12]);
+    dft4(v[1], v[5], v[9], v[13]);
+    dft4(v[2], v[6], v[10], v[14]);
+    dft4(v[3], v[7], v[11], v[15]);
+    // step 2: slot r0 + 4*q0 *= w16^{r0*q0}
+    const T c1 = (T)0.92387953251128675613, s1 = (T)0.38268343236508977173;   // cos, sin(pi/8)
+    const T h = (T)0.70710678118654752440;
+    auto mul = [](cx<T> &z, T wr, T wi) { cx<T> t = z; z.x = t.x * wr - t.y * wi; z.y = t.x * wi + t.y * wr; };
+    // q0 = 1: r0 = 1,2,3 -> w16^1, w16^2, w16^3
+    mul(v[5], c1, -s1);
+    { cx<T> t = v[6]; v[6].x = (t.x + t.y) * h; v[6].y = (t.y - t.x) * h; }
+    mul(v[7], s1, -c1);
+    // q0 = 2: w16^2, w16^4, w16^6
+    { cx<T> t = v[9]; v[9].x = (t.x + t.y) * h; v[9].y = (t.y - t.x) * h; }
+    { cx<T> t = v[10]; v[10].x = t.y; v[10].y = -t.x; }
+    { cx<T> t = v[11]; v[11].x = (t.y - t.x) * h; v[11].y = -(t.x + t.y) * h; }
+    // q0 = 3: w16^3, w16^6, w16^9
+    mul(v[13], s1, -c1);
+    { cx<T> t = v[14]; v[14].x = (t.y - t.x) * h; v[14].y = -(t.x + t.y) * h; }
+    mul(v[15], -c1, s1);
+    // step 3: for each q0, DFT4 over r0 of slots 4*q0 .. 4*q0+3 -> V[q0 + 4*q1] in slot 4*q0 + q1
+    dft4(v[0], v[1], v[2], v[3]);
+    dft4(v[4], v[5], v[6], v[7]);
+    dft4(v[8], v[9], v[10], v[11]);
+    dft4(v[12], v[13], v[14], v[15]);
+  }
+};
+// where output q of Dft<T, R>::run ends up: 8-point V[q0 + 4*q1] in slot 2*q0 + q1,
+// 16-point V[q0 + 4*q1] in slot 4*q0 + q1
+template <int R>
+__device__ constexpr int slot_of(int q) {
+  return R == 8 ? (2 * (q % 4) + q / 4) : (R == 16 ? (4 * (q % 4) + q / 4) : q);
+}
+
+__device__ __forceinline__ int sign_mod_dev(const SignModDev &m, int idx) {
+  const int g = idx + m.start;
+  if (g >= m.half) return 1;
+  return ((g & 1) ? -1 : 1) * m.extra;
+}
+
+constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x / 2); }
+
+// padded shared-memory index: one extra element every 16 keeps the radix-16 scatter conflict-free
+__device__ __forceinline__ int phys(int idx) { return idx + (idx >> 4); }
+
+template <int N>
+constexpr int line_pitch(int skew) { return N + (N >> 4) + skew; }
+
+// One Stockham pass on the E register-resident points of a line.
+//  R : radix, NS : product of the radices of earlier passes, LAST : outputs stay in registers
+template <typename T, int N, int E, int R, int NS, bool LAST>
+__device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ tw, cx<T> *line_smem) {
+  constexpr int THREADS = N / E;
+  constexpr int B = E / R;              // butterflies per thread
+  constexpr int TSTEP = N / (NS * R);   // table stride of this pass' twiddles
+#pragma unroll
+  for (int b = 0; b < B; b++) {
+    const int j = t + b * THREADS;
+    cx<T> v[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = x[b + r * B];
+    if (NS > 1) {
+      const int k = j & (NS - 1);
+#pragma unroll
+      for (int r = 1; r < R; r++) {
+        const cx<T> w = tw[k * r * TSTEP];
+        v[r] = cmul(v[r], w);
+      }
+    }
+    Dft<T, R>::run(v);
+    if (LAST) {
+#pragma unroll
+      for (int q = 0; q < R; q++) x[b + q * B] = v[slot_of<R>(q)];
+    } else {
+      const int k = j & (NS - 1);
+      const int base = ((j - k) * R) + k;   // (j / NS) * NS * R + k
+#pragma unroll
+      for (int q = 0; q < R; q++) line_smem[phys(base + q * NS)] = v[slot_of<R>(q)];
+    }
+  }
+}
+
+template <typename T, int N, int E>
+struct Passes {
+  static constexpr int R1 = E;
+  static constexpr int REM1 = N / E;
+  static constexpr int R2 = REM1 >= E ? E : REM1;
+  static constexpr int REM2 = REM1 / R2;
+  static constexpr int R3 = REM2 >= E ? E : REM2;
+  static constexpr int REM3 = REM2 / R3;
+  static_assert(REM3 == 1, "at most three passes");
+  static constexpr int NPASS = R3 > 1 ? 3 : 2;
+};
+
+template <typename T, int N, int E, int MAXT>
+__global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_kernel(const __grid_constant__ StageParams sp) {
+  using P = Passes<T, N, E>;
+  constexpr int THREADS = N / E;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
+  const cx<T> *tw = reinterpret_cast<const cx<T> *>(sp.twiddle);
+  const int tl = sp.tl;
+  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int pitch = N + (N >> 4) + skew;
+  const int tid = threadIdx.x;
+  // load mapping: along the line when the input is line-contiguous, else tile-minor
+  const bool in_line_major = sp.istride == 1;
+  const bool out_line_major = sp.ostride == 1;
+  const int t_in = in_line_major ? tid % THREADS : tid / tl;
+  const int tt_in = in_line_major ? tid / THREADS : tid % tl;
+  const int t_out = out_line_major ? tid % THREADS : tid / tl;
+  const int tt_out = out_line_major ? tid / THREADS : tid % tl;
+  const bool backward = sp.sign > 0;
+  const bool seg_in = sp.iseg_stride != 0;
+  const bool seg_out = sp.noseg > 1;
+  const bool iblk_pow2 = (sp.iblk & (sp.iblk - 1)) == 0;
+  const bool oblk_pow2 = (sp.oblk & (sp.oblk - 1)) == 0;
+  const int iblk_sh = 31 - __clz(sp.iblk), oblk_sh = 31 - __clz(sp.oblk);
+
+  for (long long tile = blockIdx.x; tile < sp.ntiles; tile += gridDim.x) {
+    long long rest = tile;
+    long long ibase = 0, obase = 0;
+    int tvalid = 1;
+    long long t_is = 0, t_os = 0;
+    if (sp.tile_dim >= 0) {
+      const long long chunk = rest % sp.tiles_along;
+      rest /= sp.tiles_along;
+      const long long first = chunk * tl;
+      const long long left = sp.bext[sp.tile_dim] - first;
+      tvalid = left < tl ? (int)left : tl;
+      t_is = sp.bis[sp.tile_dim];
+      t_os = sp.bos[sp.tile_dim];
+      ibase = first * t_is;
+      obase = first * t_os;
+    }
+#pragma unroll
+    for (int k = kMaxBatch - 1; k >= 0; k--) {
+      if (k >= sp.nbatch || k == sp.tile_dim) continue;
+      const long long c = rest % sp.bext[k];
+      rest /= sp.bext[k];
+      ibase += c * sp.bis[k];
+      obase += c * sp.bos[k];
+    }
+
+    // ---- load E points of my line into registers
+    cx<T> x[E];
+    {
+      const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
+      const bool live = tt_in < tvalid;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int idx = t_in + e * THREADS;      // position in the length-N line
+        const int j = idx - sp.zin;              // position in the input line
+        cx<T> v{(T)0, (T)0};
+        if (live && j >= 0 && j < sp.nin) {
+          long long off;
+          if (seg_in) {
+            const int seg = iblk_pow2 ? (j >> iblk_sh) : (j / sp.iblk);
+            off = (long long)seg * sp.iseg_stride + (long long)(j - seg * sp.iblk) * sp.istride;
+          } else {
+            off = (long long)j * sp.istride;
+          }
+          using V = typename C2<T>::type;
+          const V raw = __ldg(reinterpret_cast<const V *>(in + off));
+          v.x = raw.x;
+          v.y = raw.y;
+          if (sp.conj_in) v.y = -v.y;
+          if (sp.mod_in.on && sign_mod_dev(sp.mod_in, j) < 0) { v.x = -v.x; v.y = -v.y; }
+          if (backward) { T s = v.x; v.x = v.y; v.y = s; }
+        }
+        x[e] = v;
+      }
+    }
+
+    // ---- passes
+    cx<T> *line_w = smem + tt_in * pitch;    // exchange buffers are addressed per line
+    pass<T, N, E, P::R1, 1, false>(x, t_in, tw, line_w);
+    __syncthreads();
+    if (P::NPASS == 2) {
+      const cx<T> *line_r = smem + tt_out * pitch;
+#pragma unroll
+      for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
+      pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw, nullptr);
+    } else {
+      {
+        const cx<T> *line_r = smem + tt_in * pitch;
+#pragma unroll
+        for (int e = 0; e < E; e++) x[e] = line_r[phys(t_in + e * THREADS)];
+      }
+      __syncthreads();
+      pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw, line_w);
+      __syncthreads();
+      const cx<T> *line_r = smem + tt_out * pitch;
+#pragma unroll
+      for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
+      pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw, nullptr);
+    }
+
+    // ---- store the kept outputs
+    if (tt_out < tvalid) {
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const int k = t_out + e * THREADS;
+        const int kk = k - sp.zout;
+        if (kk < 0 || kk >= sp.nout) continue;
+        cx<T> v = x[e];
+        if (backward) { T s = v.x; v.x = v.y; v.y = s; }
+        if (sp.mod_out.on && sign_mod_dev(sp.mod_out, kk) < 0) { v.x = -v.x; v.y = -v.y; }
+        if (sp.conj_out) v.y = -v.y;
+        int seg = 0;
+        int kl = kk;
+        if (seg_out) {
+          seg = oblk_pow2 ? (kk >> oblk_sh) : (kk / sp.oblk);
+          kl = kk - seg * sp.oblk;
+        }
+        cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase + (long long)tt_out * t_os + (long long)kl * sp.ostride;
+        using V = typename C2<T>::type;
+        V raw;
+        raw.x = v.x;
+        raw.y = v.y;
+        *reinterpret_cast<V *>(out) = raw;
+      }
+    }
+    __syncthreads();   // exchange buffers are reused by the next tile
+  }
+}
+
+// (N, E) pairs compiled in; E = points per thread
+template <typename T>
+constexpr int max_block() { return sizeof(T) == 8 ? 256 : 512; }
+
+template <typename T, int N, int E>
+cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
+  constexpr int THREADS = N / E;
+  constexpr int MAXT = max_block<T>();
+  const int tl = sp.tl;
+  const int skew = tl <= 8 ? 8 / tl : 0;
+  const size_t smem = (size_t)tl * (N + (N >> 4) + skew) * 2 * sizeof(T);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(stage_pow2_kernel<T, N, E, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_pow2_kernel<T, N, E, MAXT>, tl * THREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  const long long grid = std::min<long long>(sp.ntiles, (long long)sms * per_sm);
+  stage_pow2_kernel<T, N, E, MAXT><<<(unsigned)grid, tl * THREADS, smem, stream>>>(sp);
+  launch_counter()++;
+  return cudaGetLastError();
+}
+
+constexpr int points_per_thread(int n) {
+  // three passes at most: 64 -> 8*8, 128 -> 8*8*2, 256 -> 16*16, 512 -> 8*8*8, 1024 -> 16*16*4, ...
+  return (n == 64 || n == 128 || n == 512) ? 8 : 16;
+}
+
+}  // namespace
+
+template <typename T>
+bool pow2_supported(const Stage &g, int L) {
+  if (g.op != OP_C2C) return false;
+  if (L < 64 || L > 4096 || (L & (L - 1))) return false;
+  if (g.in_real || g.out_real) return false;
+  if (g.noseg > kMaxSeg) return false;
+  return true;
+}
+
+template <typename T>
+int pow2_pick_tile(const Stage &g, int L) {
+  // as many lines as fit the block: a strided side then moves tl * sizeof(complex)
+  // contiguous bytes per point (64 B for fp64 / N = 1024)
+  const int threads = L / points_per_thread(L);
+  int tl = max_block<T>() / threads;
+  if (tl < 1) tl = 1;
+  if (g.tile_dim < 0) tl = 1;
+  else if ((INT)tl > g.batch[g.tile_dim].extent) {
+    tl = 1;
+    while (tl * 2 <= g.batch[g.tile_dim].extent) tl *= 2;
+  }
+  return tl;
+}
+
+template <typename T>
+cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream) {
+  if (sp.ntiles <= 0) return cudaSuccess;
+  switch (sp.L) {
+    case 64: return launch_variant<T, 64, 8>(sp, stream);
+    case 128: return launch_variant<T, 128, 8>(sp, stream);
+    case 256: return launch_variant<T, 256, 16>(sp, stream);
+    case 512: return launch_variant<T, 512, 8>(sp, stream);
+    case 1024: return launch_variant<T, 1024, 16>(sp, stream);
+    case 2048: return launch_variant<T, 2048, 16>(sp, stream);
+    case 4096: return launch_variant<T, 4096, 16>(sp, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 template bool pow2_supported<float>(const Stage &, int);
 template bool pow2_supported<double>(const Stage &, int);
 template int pow2_pick_tile<float>(const Stage &, int);
 template int pow2_pick_tile<double>(const Stage &, int);
 template cudaError_t launch_stage_pow2<float>(StageParams &, cudaStream_t);
 template cudaError_t launch_stage_pow2<double>(StageParams &, cudaStream_t);
-}
+
+}  // namespace pfb
