@@ -24,6 +24,8 @@
 // (kernel/sertrafo.c:489-554,604-646), i.e. two passes over memory; here it is one.
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "kernels.h"
 
 namespace pfb {
@@ -150,32 +152,32 @@ template <int N>
 constexpr int line_pitch(int skew) { return N + (N >> 4) + skew; }
 
 // One Stockham pass on the E register-resident points of a line.
-//  R : radix, NS : product of the radices of earlier passes, LAST : outputs stay in registers
+//  R : radix, NS : product of the radices of earlier passes, LAST : outputs stay in registers.
+//  twp : this pass' twiddles laid out [r-1][k] (k < NS), so that neighbouring threads read
+//        neighbouring entries: w_N^{k * r * N/(NS*R)}
 template <typename T, int N, int E, int R, int NS, bool LAST>
-__device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ tw, cx<T> *line_smem) {
+__device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ twp, cx<T> *line_smem) {
   constexpr int THREADS = N / E;
   constexpr int B = E / R;              // butterflies per thread
-  constexpr int TSTEP = N / (NS * R);   // table stride of this pass' twiddles
 #pragma unroll
   for (int b = 0; b < B; b++) {
     const int j = t + b * THREADS;
+    const int k = j & (NS - 1);
     cx<T> v[R];
 #pragma unroll
     for (int r = 0; r < R; r++) v[r] = x[b + r * B];
     if (NS > 1) {
-      const int k = j & (NS - 1);
+      cx<T> w[R];
 #pragma unroll
-      for (int r = 1; r < R; r++) {
-        const cx<T> w = tw[k * r * TSTEP];
-        v[r] = cmul(v[r], w);
-      }
+      for (int r = 1; r < R; r++) w[r] = twp[(r - 1) * NS + k];
+#pragma unroll
+      for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
     }
     Dft<T, R>::run(v);
     if (LAST) {
 #pragma unroll
       for (int q = 0; q < R; q++) x[b + q * B] = v[slot_of<R>(q)];
     } else {
-      const int k = j & (NS - 1);
       const int base = ((j - k) * R) + k;   // (j / NS) * NS * R + k
 #pragma unroll
       for (int q = 0; q < R; q++) line_smem[phys(base + q * NS)] = v[slot_of<R>(q)];
@@ -183,7 +185,7 @@ __device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ 
   }
 }
 
-template <typename T, int N, int E>
+template <int N, int E>
 struct Passes {
   static constexpr int R1 = E;
   static constexpr int REM1 = N / E;
@@ -195,13 +197,30 @@ struct Passes {
   static constexpr int NPASS = R3 > 1 ? 3 : 2;
 };
 
-template <typename T, int N, int E, int MAXT>
+// streaming 16-byte / 8-byte global load that does not allocate in L1 (the twiddle tables live there)
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {
+  float2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+  return r;
+}
+
+// FAST: no pruning, no index-shift modulation, chunk boundaries aligned with the thread
+// distribution -> every address is  base(thread, tile) + table[e]  with the table in the
+// constant bank.  Otherwise the general (integer-division) addressing is used.
+template <typename T, int N, int E, int MAXT, bool FAST>
 __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_kernel(const __grid_constant__ StageParams sp) {
-  using P = Passes<T, N, E>;
+  using P = Passes<N, E>;
+  using V = typename C2<T>::type;
   constexpr int THREADS = N / E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
-  const cx<T> *tw = reinterpret_cast<const cx<T> *>(sp.twiddle);
+  const cx<T> *tw2 = reinterpret_cast<const cx<T> *>(sp.tw2);
+  const cx<T> *tw3 = reinterpret_cast<const cx<T> *>(sp.tw3);
   const int tl = sp.tl;
   const int skew = tl <= 8 ? 8 / tl : 0;
   const int pitch = N + (N >> 4) + skew;
@@ -214,21 +233,19 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
   const int t_out = out_line_major ? tid % THREADS : tid / tl;
   const int tt_out = out_line_major ? tid / THREADS : tid % tl;
   const bool backward = sp.sign > 0;
-  const bool seg_in = sp.iseg_stride != 0;
-  const bool seg_out = sp.noseg > 1;
-  const bool iblk_pow2 = (sp.iblk & (sp.iblk - 1)) == 0;
-  const bool oblk_pow2 = (sp.oblk & (sp.oblk - 1)) == 0;
-  const int iblk_sh = 31 - __clz(sp.iblk), oblk_sh = 31 - __clz(sp.oblk);
 
-  for (long long tile = blockIdx.x; tile < sp.ntiles; tile += gridDim.x) {
-    long long rest = tile;
+  // tile bookkeeping in 32 bits (the host refuses the fast kernels beyond 2^31 tiles)
+  const unsigned ntiles = (unsigned)sp.ntiles;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned rest = tile;
     long long ibase = 0, obase = 0;
     int tvalid = 1;
     long long t_is = 0, t_os = 0;
     if (sp.tile_dim >= 0) {
-      const long long chunk = rest % sp.tiles_along;
-      rest /= sp.tiles_along;
-      const long long first = chunk * tl;
+      const unsigned along = (unsigned)sp.tiles_along;
+      const unsigned chunk = rest % along;
+      rest /= along;
+      const long long first = (long long)chunk * tl;
       const long long left = sp.bext[sp.tile_dim] - first;
       tvalid = left < tl ? (int)left : tl;
       t_is = sp.bis[sp.tile_dim];
@@ -239,51 +256,72 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
 #pragma unroll
     for (int k = kMaxBatch - 1; k >= 0; k--) {
       if (k >= sp.nbatch || k == sp.tile_dim) continue;
-      const long long c = rest % sp.bext[k];
-      rest /= sp.bext[k];
-      ibase += c * sp.bis[k];
-      obase += c * sp.bos[k];
+      const unsigned ext = (unsigned)sp.bext[k];
+      const unsigned c = rest % ext;
+      rest /= ext;
+      ibase += (long long)c * sp.bis[k];
+      obase += (long long)c * sp.bos[k];
     }
 
-    // ---- load E points of my line into registers
+    // ---- load E points of my line into registers: all loads are issued before any of
+    // them is consumed (E independent 16-byte requests in flight per thread)
     cx<T> x[E];
     {
-      const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
       const bool live = tt_in < tvalid;
+      V raw[E];
+      if (FAST) {
+        const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is + (long long)t_in * sp.istride;
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int idx = t_in + e * THREADS;      // position in the length-N line
-        const int j = idx - sp.zin;              // position in the input line
-        cx<T> v{(T)0, (T)0};
-        if (live && j >= 0 && j < sp.nin) {
+        for (int e = 0; e < E; e++) {
+          V r;
+          r.x = (T)0;
+          r.y = (T)0;
+          if (live) r = ld_stream(reinterpret_cast<const V *>(in + sp.in_off[e]));
+          raw[e] = r;
+        }
+      } else {
+        const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
+        const bool seg_in = sp.iseg_stride != 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int j = t_in + e * THREADS - sp.zin;   // position in the input line
           long long off;
           if (seg_in) {
-            const int seg = iblk_pow2 ? (j >> iblk_sh) : (j / sp.iblk);
-            off = (long long)seg * sp.iseg_stride + (long long)(j - seg * sp.iblk) * sp.istride;
+            const int jj = j < 0 ? 0 : j;
+            const int seg = jj / sp.iblk;
+            off = (long long)seg * sp.iseg_stride + (long long)(jj - seg * sp.iblk) * sp.istride;
           } else {
             off = (long long)j * sp.istride;
           }
-          using V = typename C2<T>::type;
-          const V raw = __ldg(reinterpret_cast<const V *>(in + off));
-          v.x = raw.x;
-          v.y = raw.y;
-          if (sp.conj_in) v.y = -v.y;
-          if (sp.mod_in.on && sign_mod_dev(sp.mod_in, j) < 0) { v.x = -v.x; v.y = -v.y; }
-          if (backward) { T s = v.x; v.x = v.y; v.y = s; }
+          const bool ok = live && j >= 0 && j < sp.nin;
+          V r;
+          r.x = (T)0;
+          r.y = (T)0;
+          if (ok) r = ld_stream(reinterpret_cast<const V *>(in + off));
+          raw[e] = r;
         }
-        x[e] = v;
+      }
+      const bool cj = sp.conj_in != 0;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        T re = raw[e].x, im = cj ? -raw[e].y : raw[e].y;
+        if (!FAST && sp.mod_in.on) {
+          if (sign_mod_dev(sp.mod_in, t_in + e * THREADS - sp.zin) < 0) { re = -re; im = -im; }
+        }
+        x[e].x = backward ? im : re;
+        x[e].y = backward ? re : im;
       }
     }
 
     // ---- passes
     cx<T> *line_w = smem + tt_in * pitch;    // exchange buffers are addressed per line
-    pass<T, N, E, P::R1, 1, false>(x, t_in, tw, line_w);
+    pass<T, N, E, P::R1, 1, false>(x, t_in, nullptr, line_w);
     __syncthreads();
     if (P::NPASS == 2) {
       const cx<T> *line_r = smem + tt_out * pitch;
 #pragma unroll
       for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
-      pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw, nullptr);
+      pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw2, nullptr);
     } else {
       {
         const cx<T> *line_r = smem + tt_in * pitch;
@@ -291,47 +329,57 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
         for (int e = 0; e < E; e++) x[e] = line_r[phys(t_in + e * THREADS)];
       }
       __syncthreads();
-      pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw, line_w);
+      pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw2, line_w);
       __syncthreads();
       const cx<T> *line_r = smem + tt_out * pitch;
 #pragma unroll
       for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
-      pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw, nullptr);
+      pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw3, nullptr);
     }
 
     // ---- store the kept outputs
     if (tt_out < tvalid) {
+      const bool cj = sp.conj_out != 0;
+      if (FAST) {
+        const long long thread_off = obase + (long long)tt_out * t_os + (long long)t_out * sp.ostride;
 #pragma unroll
-      for (int e = 0; e < E; e++) {
-        const int k = t_out + e * THREADS;
-        const int kk = k - sp.zout;
-        if (kk < 0 || kk >= sp.nout) continue;
-        cx<T> v = x[e];
-        if (backward) { T s = v.x; v.x = v.y; v.y = s; }
-        if (sp.mod_out.on && sign_mod_dev(sp.mod_out, kk) < 0) { v.x = -v.x; v.y = -v.y; }
-        if (sp.conj_out) v.y = -v.y;
-        int seg = 0;
-        int kl = kk;
-        if (seg_out) {
-          seg = oblk_pow2 ? (kk >> oblk_sh) : (kk / sp.oblk);
-          kl = kk - seg * sp.oblk;
+        for (int e = 0; e < E; e++) {
+          V raw;
+          raw.x = backward ? x[e].y : x[e].x;
+          raw.y = backward ? x[e].x : x[e].y;
+          if (cj) raw.y = -raw.y;
+          cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[sp.out_seg[e]]) + thread_off + sp.out_off[e];
+          *reinterpret_cast<V *>(out) = raw;
         }
-        cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase + (long long)tt_out * t_os + (long long)kl * sp.ostride;
-        using V = typename C2<T>::type;
-        V raw;
-        raw.x = v.x;
-        raw.y = v.y;
-        *reinterpret_cast<V *>(out) = raw;
+      } else {
+        const bool seg_out = sp.noseg > 1;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+          const int kk = t_out + e * THREADS - sp.zout;
+          if (kk < 0 || kk >= sp.nout) continue;
+          V raw;
+          raw.x = backward ? x[e].y : x[e].x;
+          raw.y = backward ? x[e].x : x[e].y;
+          if (sp.mod_out.on && sign_mod_dev(sp.mod_out, kk) < 0) { raw.x = -raw.x; raw.y = -raw.y; }
+          if (cj) raw.y = -raw.y;
+          int seg = 0, kl = kk;
+          if (seg_out) {
+            seg = kk / sp.oblk;
+            kl = kk - seg * sp.oblk;
+          }
+          cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase + (long long)tt_out * t_os + (long long)kl * sp.ostride;
+          *reinterpret_cast<V *>(out) = raw;
+        }
       }
     }
     __syncthreads();   // exchange buffers are reused by the next tile
   }
 }
 
-// (N, E) pairs compiled in; E = points per thread
 template <typename T>
 constexpr int max_block() { return sizeof(T) == 8 ? 256 : 512; }
 
+// (N, E) pairs compiled in; E = points per thread
 template <typename T, int N, int E>
 cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   constexpr int THREADS = N / E;
@@ -339,9 +387,13 @@ cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   const int tl = sp.tl;
   const int skew = tl <= 8 ? 8 / tl : 0;
   const size_t smem = (size_t)tl * (N + (N >> 4) + skew) * 2 * sizeof(T);
+  auto fast = stage_pow2_kernel<T, N, E, MAXT, true>;
+  auto slow = stage_pow2_kernel<T, N, E, MAXT, false>;
+  auto kern = sp.fast ? fast : slow;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(stage_pow2_kernel<T, N, E, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(slow, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -349,10 +401,10 @@ cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stage_pow2_kernel<T, N, E, MAXT>, tl * THREADS, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl * THREADS, smem);
   if (per_sm < 1) per_sm = 1;
   const long long grid = std::min<long long>(sp.ntiles, (long long)sms * per_sm);
-  stage_pow2_kernel<T, N, E, MAXT><<<(unsigned)grid, tl * THREADS, smem, stream>>>(sp);
+  kern<<<(unsigned)grid, tl * THREADS, smem, stream>>>(sp);
   launch_counter()++;
   return cudaGetLastError();
 }
@@ -370,6 +422,12 @@ bool pow2_supported(const Stage &g, int L) {
   if (L < 64 || L > 4096 || (L & (L - 1))) return false;
   if (g.in_real || g.out_real) return false;
   if (g.noseg > kMaxSeg) return false;
+  long long lines = 1;
+  for (int k = 0; k < g.nbatch; k++) {
+    if (g.batch[k].extent >= (1ll << 31)) return false;
+    lines *= g.batch[k].extent;
+  }
+  if (lines >= (1ll << 31)) return false;
   return true;
 }
 
@@ -403,11 +461,70 @@ cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream) {
   }
 }
 
+// Decide whether the table-driven addressing applies and fill the tables.
+template <typename T>
+void pow2_prepare(const Stage &g, StageParams &sp) {
+  const int L = sp.L;
+  const int E = points_per_thread(L);
+  const int threads = L / E;
+  bool fast = g.nin == L && g.zin == 0 && g.nout == L && g.zout == 0 && !g.mod_in.on && !g.mod_out.on;
+  const bool seg_in = g.iseg_stride != 0 && g.iblk < g.nin;
+  const bool seg_out = g.noseg > 1;
+  if (seg_in && g.iblk % threads != 0) fast = false;
+  if (seg_out && g.oblk % threads != 0) fast = false;
+  sp.fast = fast ? 1 : 0;
+  if (!fast) return;
+  for (int e = 0; e < E; e++) {
+    const long long idx = (long long)e * threads;
+    if (seg_in) {
+      const long long seg = idx / g.iblk;
+      sp.in_off[e] = seg * g.iseg_stride + (idx - seg * g.iblk) * g.istride;
+    } else {
+      sp.in_off[e] = idx * g.istride;
+    }
+    if (seg_out) {
+      const long long seg = idx / g.oblk;
+      sp.out_seg[e] = (int)seg;
+      sp.out_off[e] = (idx - seg * g.oblk) * g.ostride;
+    } else {
+      sp.out_seg[e] = 0;
+      sp.out_off[e] = idx * g.ostride;
+    }
+  }
+}
+
+// Per-pass twiddle tables [r-1][k]: returns element offsets of the pass-2 / pass-3 tables
+// inside `table` (complex entries, forward sign).
+void pow2_twiddle_tables(int L, const double *roots /* 2*L */, std::vector<double> *table, size_t *off2, size_t *off3) {
+  const int E = points_per_thread(L);
+  int rem = L / E;
+  const int R1 = E;
+  const int R2 = rem >= E ? E : rem;
+  rem /= R2;
+  const int R3 = rem;
+  table->clear();
+  auto emit = [&](int NS, int R) {
+    const int tstep = L / (NS * R);
+    for (int r = 1; r < R; r++)
+      for (int k = 0; k < NS; k++) {
+        const long long idx = (long long)k * r * tstep;
+        table->push_back(roots[2 * idx]);
+        table->push_back(roots[2 * idx + 1]);
+      }
+  };
+  *off2 = 0;
+  emit(R1, R2);
+  *off3 = table->size() / 2;
+  if (R3 > 1) emit(R1 * R2, R3);
+}
+
 template bool pow2_supported<float>(const Stage &, int);
 template bool pow2_supported<double>(const Stage &, int);
 template int pow2_pick_tile<float>(const Stage &, int);
 template int pow2_pick_tile<double>(const Stage &, int);
 template cudaError_t launch_stage_pow2<float>(StageParams &, cudaStream_t);
 template cudaError_t launch_stage_pow2<double>(StageParams &, cudaStream_t);
+template void pow2_prepare<float>(const Stage &, StageParams &);
+template void pow2_prepare<double>(const Stage &, StageParams &);
 
 }  // namespace pfb

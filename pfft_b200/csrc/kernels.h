@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "core.h"
 
 namespace pfb {
@@ -36,6 +38,12 @@ struct StageParams {
   const void *twiddle;       // L entries exp(-2*pi*i*k/L) in the stage's precision
   int nfac;
   int fac[kMaxFactors];
+  // power-of-two fast path (fft_pow2.cu)
+  int fast;                  // table-driven addressing applies
+  const void *tw2, *tw3;     // per-pass twiddle tables [r-1][k]
+  long long in_off[16];      // element offset of line index e*THREADS on input
+  long long out_off[16];     // ... on output, inside chunk out_seg[e]
+  int out_seg[16];
 };
 
 // host-side helpers (fft_tables.cpp)
@@ -56,6 +64,9 @@ template <typename T>
 cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream);
 template <typename T>
 int pow2_pick_tile(const Stage &g, int L);
+template <typename T>
+void pow2_prepare(const Stage &g, StageParams &sp);
+void pow2_twiddle_tables(int L, const double *roots, std::vector<double> *table, size_t *off2, size_t *off3);
 
 unsigned long long &launch_counter();
 

@@ -87,7 +87,12 @@ static bool all_ranks_ok(MPI_Comm comm, bool ok) {
 
 template <typename T>
 static bool build_stage_params(PlanBase *pl, std::string *err) {
-  std::map<int, void *> table_of;
+  struct TableSet {
+    void *dev;
+    size_t off2, off3;
+    bool has_pow2;
+  };
+  std::map<int, TableSet> table_of;
   const Schedule &s = pl->sched;
   for (size_t i = 0; i < s.stages.size(); i++) {
     const Stage &g = s.stages[i];
@@ -143,18 +148,34 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     if (g.nout == 0 || lines == 0) sp.ntiles = 0;
     sp.nfac = factorize_generic(L, sp.fac);
     if (g.op != OP_COPY) {
-      auto it = table_of.find(L);
+      auto it = table_of.find(2 * L + (fast ? 1 : 0));
       if (it == table_of.end()) {
-        std::vector<T> host(2 * (size_t)L);
-        if (sizeof(T) == 8) make_twiddles_f64(L, reinterpret_cast<double *>(host.data()));
-        else make_twiddles_f32(L, reinterpret_cast<float *>(host.data()));
+        // unit roots in fp64 (< 1 ulp), then the layouts the kernels want, rounded once to T
+        std::vector<double> roots(2 * (size_t)L);
+        make_twiddles_f64(L, roots.data());
+        std::vector<double> all(roots);
+        size_t off2 = 0, off3 = 0;
+        if (fast) {
+          std::vector<double> pp;
+          pow2_twiddle_tables(L, roots.data(), &pp, &off2, &off3);
+          off2 += L;
+          off3 += L;
+          all.insert(all.end(), pp.begin(), pp.end());
+        }
+        std::vector<T> host(all.begin(), all.end());
         void *dev = nullptr;
         CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(T)));
         CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
         pl->tables.push_back(dev);
-        it = table_of.emplace(L, dev).first;
+        it = table_of.emplace(2 * L + (fast ? 1 : 0), TableSet{dev, off2, off3, fast}).first;
       }
-      sp.twiddle = it->second;
+      const TableSet &ts = it->second;
+      sp.twiddle = ts.dev;
+      if (fast) {
+        sp.tw2 = static_cast<const T *>(ts.dev) + 2 * ts.off2;
+        sp.tw3 = static_cast<const T *>(ts.dev) + 2 * ts.off3;
+        pow2_prepare<T>(g, sp);
+      }
     }
     pl->params.push_back(sp);
     pl->use_pow2.push_back(fast ? 1 : 0);
