@@ -167,11 +167,17 @@ __device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ 
 #pragma unroll
     for (int r = 0; r < R; r++) v[r] = x[b + r * B];
     if (NS > 1) {
-      cx<T> w[R];
+      // twiddles come from shared memory, four at a time (keeps register pressure down)
 #pragma unroll
-      for (int r = 1; r < R; r++) w[r] = twp[(r - 1) * NS + k];
+      for (int r0 = 1; r0 < R; r0 += 4) {
+        cx<T> w[4];
 #pragma unroll
-      for (int r = 1; r < R; r++) v[r] = cmul(v[r], w[r]);
+        for (int i = 0; i < 4; i++)
+          if (r0 + i < R) w[i] = twp[(r0 + i - 1) * NS + k];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+          if (r0 + i < R) v[r0 + i] = cmul(v[r0 + i], w[i]);
+      }
     }
     Dft<T, R>::run(v);
     if (LAST) {
@@ -209,6 +215,16 @@ __device__ __forceinline__ float2 ld_stream(const float2 *p) {
   return r;
 }
 
+// cp.async of BYTES (8 or 16) global -> shared; `ok == false` writes zeros instead (src-size 0)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(unsigned dst_smem, const void *src, bool ok) {
+  const int n = ok ? BYTES : 0;
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+
 // FAST: no pruning, no index-shift modulation, chunk boundaries aligned with the thread
 // distribution -> every address is  base(thread, tile) + table[e]  with the table in the
 // constant bank.  Otherwise the general (integer-division) addressing is used.
@@ -219,12 +235,22 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
   constexpr int THREADS = N / E;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
-  const cx<T> *tw2 = reinterpret_cast<const cx<T> *>(sp.tw2);
-  const cx<T> *tw3 = reinterpret_cast<const cx<T> *>(sp.tw3);
   const int tl = sp.tl;
   const int skew = tl <= 8 ? 8 / tl : 0;
   const int pitch = N + (N >> 4) + skew;
   const int tid = threadIdx.x;
+  // per-pass twiddle tables live in shared memory behind the exchange buffer (persistent CTA:
+  // loaded once): pass 2 has (R2-1)*R1 entries, pass 3 has (R3-1)*R1*R2
+  constexpr int TW2 = (P::R2 - 1) * P::R1;
+  constexpr int TW3 = P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0;
+  cx<T> *tw_s = smem + (size_t)tl * pitch;
+  {
+    const cx<T> *g2 = reinterpret_cast<const cx<T> *>(sp.tw2);
+    for (int i = tid; i < TW2 + TW3; i += blockDim.x) tw_s[i] = g2[i];   // the two tables are contiguous
+  }
+  const cx<T> *tw2 = tw_s;
+  const cx<T> *tw3 = tw_s + TW2;
+  __syncthreads();
   // load mapping: along the line when the input is line-contiguous, else tile-minor
   const bool in_line_major = sp.istride == 1;
   const bool out_line_major = sp.ostride == 1;
@@ -236,11 +262,11 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
 
   // tile bookkeeping in 32 bits (the host refuses the fast kernels beyond 2^31 tiles)
   const unsigned ntiles = (unsigned)sp.ntiles;
-  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  auto locate = [&](unsigned tile, long long &ibase, long long &obase, int &tvalid) {
     unsigned rest = tile;
-    long long ibase = 0, obase = 0;
-    int tvalid = 1;
-    long long t_is = 0, t_os = 0;
+    ibase = 0;
+    obase = 0;
+    tvalid = 1;
     if (sp.tile_dim >= 0) {
       const unsigned along = (unsigned)sp.tiles_along;
       const unsigned chunk = rest % along;
@@ -248,10 +274,8 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
       const long long first = (long long)chunk * tl;
       const long long left = sp.bext[sp.tile_dim] - first;
       tvalid = left < tl ? (int)left : tl;
-      t_is = sp.bis[sp.tile_dim];
-      t_os = sp.bos[sp.tile_dim];
-      ibase = first * t_is;
-      obase = first * t_os;
+      ibase = first * sp.bis[sp.tile_dim];
+      obase = first * sp.bos[sp.tile_dim];
     }
 #pragma unroll
     for (int k = kMaxBatch - 1; k >= 0; k--) {
@@ -262,49 +286,63 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
       ibase += (long long)c * sp.bis[k];
       obase += (long long)c * sp.bos[k];
     }
+  };
+  const long long t_is = sp.tile_dim >= 0 ? sp.bis[sp.tile_dim] : 0;
+  const long long t_os = sp.tile_dim >= 0 ? sp.bos[sp.tile_dim] : 0;
+  cx<T> *const my_line_in = smem + tt_in * pitch;
+  const unsigned my_line_in_s = (unsigned)__cvta_generic_to_shared(my_line_in);
 
-    // ---- load E points of my line into registers: all loads are issued before any of
-    // them is consumed (E independent 16-byte requests in flight per thread)
-    cx<T> x[E];
-    {
-      const bool live = tt_in < tvalid;
-      V raw[E];
-      if (FAST) {
-        const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is + (long long)t_in * sp.istride;
+  // Asynchronous fetch (cp.async, L2 only) of a tile's inputs into the exchange buffer: every
+  // thread fetches exactly the E points it will consume, so only cp.async.wait_all is needed
+  // before reading them back.  Missing points (padding, lines beyond a ragged tile) are zero-filled.
+  auto prefetch = [&](long long ibase, int tvalid) {
+    const bool live = tt_in < tvalid;
+    if (FAST) {
+      const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is + (long long)t_in * sp.istride;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-          V r;
-          r.x = (T)0;
-          r.y = (T)0;
-          if (live) r = ld_stream(reinterpret_cast<const V *>(in + sp.in_off[e]));
-          raw[e] = r;
-        }
-      } else {
-        const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
-        const bool seg_in = sp.iseg_stride != 0;
+      for (int e = 0; e < E; e++)
+        cp_async_zfill<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)),
+                                      live ? (const void *)(in + sp.in_off[e]) : sp.in, live);
+    } else {
+      const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
+      const bool seg_in = sp.iseg_stride != 0;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-          const int j = t_in + e * THREADS - sp.zin;   // position in the input line
-          long long off;
+      for (int e = 0; e < E; e++) {
+        const int j = t_in + e * THREADS - sp.zin;   // position in the input line
+        const bool ok = live && j >= 0 && j < sp.nin;
+        long long off = 0;
+        if (ok) {
           if (seg_in) {
-            const int jj = j < 0 ? 0 : j;
-            const int seg = jj / sp.iblk;
-            off = (long long)seg * sp.iseg_stride + (long long)(jj - seg * sp.iblk) * sp.istride;
+            const int seg = j / sp.iblk;
+            off = (long long)seg * sp.iseg_stride + (long long)(j - seg * sp.iblk) * sp.istride;
           } else {
             off = (long long)j * sp.istride;
           }
-          const bool ok = live && j >= 0 && j < sp.nin;
-          V r;
-          r.x = (T)0;
-          r.y = (T)0;
-          if (ok) r = ld_stream(reinterpret_cast<const V *>(in + off));
-          raw[e] = r;
         }
+        cp_async_zfill<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)),
+                                      ok ? (const void *)(in + off) : sp.in, ok);
       }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  long long ibase, obase;
+  int tvalid;
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) {
+    locate(tile, ibase, obase, tvalid);
+    prefetch(ibase, tvalid);
+  }
+  for (; tile < ntiles; tile += gridDim.x) {
+    // ---- my E points: wait for the asynchronous fetch, pick them up from shared memory
+    cx<T> x[E];
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    {
       const bool cj = sp.conj_in != 0;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        T re = raw[e].x, im = cj ? -raw[e].y : raw[e].y;
+        const cx<T> r = my_line_in[phys(t_in + e * THREADS)];
+        T re = r.x, im = cj ? -r.y : r.y;
         if (!FAST && sp.mod_in.on) {
           if (sign_mod_dev(sp.mod_in, t_in + e * THREADS - sp.zin) < 0) { re = -re; im = -im; }
         }
@@ -312,36 +350,45 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
         x[e].y = backward ? re : im;
       }
     }
+    __syncthreads();   // all inputs are in registers: the buffer may be overwritten by pass 1
 
     // ---- passes
-    cx<T> *line_w = smem + tt_in * pitch;    // exchange buffers are addressed per line
+    cx<T> *line_w = my_line_in;    // exchange buffers are addressed per line
     pass<T, N, E, P::R1, 1, false>(x, t_in, nullptr, line_w);
     __syncthreads();
-    if (P::NPASS == 2) {
-      const cx<T> *line_r = smem + tt_out * pitch;
-#pragma unroll
-      for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
-      pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw2, nullptr);
-    } else {
+    if (P::NPASS == 3) {
       {
-        const cx<T> *line_r = smem + tt_in * pitch;
+        const cx<T> *line_r = my_line_in;
 #pragma unroll
         for (int e = 0; e < E; e++) x[e] = line_r[phys(t_in + e * THREADS)];
       }
       __syncthreads();
       pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw2, line_w);
       __syncthreads();
+    }
+    {
       const cx<T> *line_r = smem + tt_out * pitch;
 #pragma unroll
       for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
-      pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw3, nullptr);
     }
+    __syncthreads();   // exchange buffer is free again: start fetching the next tile behind the last pass
+    const long long obase_cur = obase;
+    const int tvalid_cur = tvalid;
+    {
+      const unsigned next = tile + gridDim.x;
+      if (next < ntiles) {
+        locate(next, ibase, obase, tvalid);
+        prefetch(ibase, tvalid);
+      }
+    }
+    if (P::NPASS == 3) pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw3, nullptr);
+    else pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw2, nullptr);
 
     // ---- store the kept outputs
-    if (tt_out < tvalid) {
+    if (tt_out < tvalid_cur) {
       const bool cj = sp.conj_out != 0;
       if (FAST) {
-        const long long thread_off = obase + (long long)tt_out * t_os + (long long)t_out * sp.ostride;
+        const long long thread_off = obase_cur + (long long)tt_out * t_os + (long long)t_out * sp.ostride;
 #pragma unroll
         for (int e = 0; e < E; e++) {
           V raw;
@@ -367,12 +414,11 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
             seg = kk / sp.oblk;
             kl = kk - seg * sp.oblk;
           }
-          cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase + (long long)tt_out * t_os + (long long)kl * sp.ostride;
+          cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase_cur + (long long)tt_out * t_os + (long long)kl * sp.ostride;
           *reinterpret_cast<V *>(out) = raw;
         }
       }
     }
-    __syncthreads();   // exchange buffers are reused by the next tile
   }
 }
 
@@ -386,7 +432,9 @@ cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   constexpr int MAXT = max_block<T>();
   const int tl = sp.tl;
   const int skew = tl <= 8 ? 8 / tl : 0;
-  const size_t smem = (size_t)tl * (N + (N >> 4) + skew) * 2 * sizeof(T);
+  using P = Passes<N, E>;
+  constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
+  const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
   auto fast = stage_pow2_kernel<T, N, E, MAXT, true>;
   auto slow = stage_pow2_kernel<T, N, E, MAXT, false>;
   auto kern = sp.fast ? fast : slow;

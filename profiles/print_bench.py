@@ -1,0 +1,8 @@
+import sys,json
+for line in sys.stdin:
+    line=line.strip()
+    if not line.startswith('{'): 
+        print(line[:300]); continue
+    d=json.loads(line)
+    r=d["roofline"]
+    print("%s: %.0f GFlop/s  %.2f ms/step frac=%.3f fwd=%s bwd=%s err=%.1e e2e=%s"%(d["config"]["workload"][:12], d["value"], d["ms_per_step"], r["frac"], [round(x,2) for x in r["stage_ms_forward"]], [round(x,2) for x in r["stage_ms_backward"]], d["roundtrip_rel_err"], d.get("e2e",{}).get("value")))
