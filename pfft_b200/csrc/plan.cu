@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 
 #include "plan.h"
@@ -227,9 +228,30 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
   if (tr == TR_AUTO) tr = TR_P2P;
   pl->transport = tr;
   const size_t nst = s.stages.size();
-  if (nst >= 2) CUDA_OK(cudaMalloc(&pl->scratch[0], pl->scratch_bytes));
-  if (nst >= 3) CUDA_OK(cudaMalloc(&pl->scratch[1], pl->scratch_bytes));
-  if (any_exchange && tr == TR_NCCL) CUDA_OK(cudaMalloc(&pl->scratch[2], pl->scratch_bytes));
+  // footprint (bytes) of what sits between stage i and stage i+1
+  pl->boundary_bytes.assign(nst > 0 ? nst - 1 : 0, 0);
+  pl->boundary_remote.assign(nst > 0 ? nst - 1 : 0, 0);
+  for (size_t i = 0; i + 1 < nst; i++) {
+    const Stage &g = s.stages[i];
+    const size_t es = rb * (g.out_real ? 1 : 2);
+    INT elems = 0;
+    for (int q = 0; q < g.noseg; q++) elems += g.oseg_cnt[q];
+    if (g.exchange >= 0) {
+      const Exchange &x = s.exchanges[g.exchange];
+      elems = std::max<INT>(elems, x.recv_cnt * x.nparts);
+      pl->boundary_remote[i] = x.nparts > 1;
+    }
+    pl->boundary_bytes[i] = (size_t)elems * es;
+  }
+  // plans with real exchanges own their receive areas from the start (peers map them);
+  // purely local plans borrow user buffers where they can and allocate scratch lazily
+  if (any_exchange) {
+    if (nst >= 2) CUDA_OK(cudaMalloc(&pl->scratch[0], pl->scratch_bytes));
+    if (nst >= 3) CUDA_OK(cudaMalloc(&pl->scratch[1], pl->scratch_bytes));
+    if (tr == TR_NCCL) CUDA_OK(cudaMalloc(&pl->scratch[2], pl->scratch_bytes));
+    pl->scratch_cap[0] = pl->scratch[0] ? pl->scratch_bytes : 0;
+    pl->scratch_cap[1] = pl->scratch[1] ? pl->scratch_bytes : 0;
+  }
   if (any_exchange) {
     std::string terr;
     bool tok = transport_setup(pl, &terr);
@@ -255,8 +277,6 @@ void plan_destroy(PlanBase *pl) {
   for (void *t : pl->tables) cudaFree(t);
   for (int k = 0; k < 3; k++)
     if (pl->scratch[k]) cudaFree(pl->scratch[k]);
-  if (pl->stage_in) cudaFree(pl->stage_in);
-  if (pl->stage_out) cudaFree(pl->stage_out);
   for (int t = 0; t < kMaxMesh; t++)
     if (pl->comm_1d[t] != MPI_COMM_NULL) MPI_Comm_free(&pl->comm_1d[t]);
   if (pl->comm_cart != MPI_COMM_NULL) MPI_Comm_free(&pl->comm_cart);
@@ -274,39 +294,122 @@ static bool device_accessible(const void *p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// Process-wide staging areas for host-pointer executes (0: input, 1: output); grow only.
+static void *staging_area(int which, size_t bytes, cudaStream_t st) {
+  static void *area[2] = {nullptr, nullptr};
+  static size_t cap[2] = {0, 0};
+  if (cap[which] < bytes) {
+    CUDA_OK(cudaStreamSynchronize(st));
+    CUDA_OK(cudaDeviceSynchronize());
+    if (area[which]) cudaFree(area[which]);
+    CUDA_OK(cudaMalloc(&area[which], bytes));
+    cap[which] = bytes;
+  }
+  return area[which];
+}
+
+// Choose, for every boundary between two stages, the buffer that holds it.  A stage never
+// writes the buffer it reads; the last intermediate is never the output array; boundaries
+// that an exchange fills are plan-owned scratch (peers map them); user arrays are used only
+// when they are large enough, and the input array only when it may be destroyed
+// (PFFT_DESTROY_INPUT, in-place, or staged host input) -- the default PFFT_PRESERVE_INPUT
+// semantics of the reference (kernel/partrafo.c:963-975) therefore holds by construction.
+// Among the feasible assignments the one with the least scratch memory wins.
+static void assign_buffers(PlanBase *pl, bool inplace, bool destroyable) {
+  const int key = (inplace ? 1 : 0) | (destroyable ? 2 : 0);
+  if (pl->assign_key == key && !pl->assign.empty()) return;
+  const size_t nb = pl->boundary_bytes.size();
+  bool any_remote = false;
+  for (size_t i = 0; i < nb; i++) any_remote |= pl->boundary_remote[i] != 0;
+  if (any_remote) {
+    // peers store into these areas: every rank must pick the same ones, whatever its block sizes
+    pl->assign.resize(nb);
+    for (size_t i = 0; i < nb; i++) pl->assign[i] = (i % 2) ? BUF_B : BUF_A;
+    pl->assign_key = key;
+    return;
+  }
+  std::vector<int> best, cur(nb, 0);
+  int best_cost = 1 << 30;
+  const int cand[4] = {BUF_USER_IN, BUF_USER_OUT, BUF_A, BUF_B};
+  std::function<void(size_t, int)> rec = [&](size_t i, int used_mask) {
+    const int cost = ((used_mask >> BUF_A) & 1) + ((used_mask >> BUF_B) & 1);
+    if (cost >= best_cost) return;
+    if (i == nb) {
+      best = cur;
+      best_cost = cost;
+      return;
+    }
+    const int prev = i == 0 ? BUF_USER_IN : cur[i - 1];
+    for (int c : cand) {
+      int id = c;
+      if (inplace && id == BUF_USER_OUT) continue;                  // same array as BUF_USER_IN
+      if (id == prev) continue;
+      if (inplace && prev == BUF_USER_IN && id == BUF_USER_IN) continue;
+      if (i + 1 == nb && (id == BUF_USER_OUT || (inplace && id == BUF_USER_IN))) continue;
+      if (pl->boundary_remote[i] && id < BUF_A) continue;
+      if (id == BUF_USER_IN && (!destroyable || pl->boundary_bytes[i] > pl->user_in_bytes)) continue;
+      if (id == BUF_USER_OUT && pl->boundary_bytes[i] > pl->user_out_bytes) continue;
+      if (id == BUF_B && !((used_mask >> BUF_A) & 1)) continue;     // symmetry: take A before B
+      cur[i] = id;
+      rec(i + 1, used_mask | (1 << id));
+    }
+  };
+  rec(0, 0);
+  if (best.size() != nb) {   // cannot happen: A/B alternation is always feasible
+    best.assign(nb, BUF_A);
+    for (size_t i = 0; i < nb; i++) best[i] = (i % 2) ? BUF_B : BUF_A;
+  }
+  pl->assign = best;
+  pl->assign_key = key;
+  // scratch on demand (plans with exchanges allocated theirs up front)
+  for (int k = 0; k < 2; k++) {
+    size_t need = 0;
+    for (size_t i = 0; i < nb; i++)
+      if (best[i] == BUF_A + k) need = std::max(need, pl->boundary_bytes[i]);
+    if (need > pl->scratch_cap[k]) {
+      CUDA_OK(cudaStreamSynchronize(pl->stream));
+      if (pl->scratch[k]) cudaFree(pl->scratch[k]);
+      CUDA_OK(cudaMalloc(&pl->scratch[k], need));
+      pl->scratch_cap[k] = need;
+    }
+  }
+}
+
 void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
   const Schedule &s = pl->sched;
   cudaStream_t st = pl->stream;
   if (!in) in = pl->planned_in;
   if (!out) out = pl->planned_out;
-  // host pointers are staged through device memory (counted in the end-to-end numbers)
+  // host pointers are staged through device memory (counted in the end-to-end numbers);
+  // the staging areas are process-wide and shared by all plans
   void *dev_in = in, *dev_out = out;
-  bool copy_back = false;
+  bool copy_back = false, staged_in = false;
   if (pl->user_in_bytes && !device_accessible(in)) {
-    if (pl->stage_in_bytes < pl->user_in_bytes) {
-      if (pl->stage_in) cudaFree(pl->stage_in);
-      CUDA_OK(cudaMalloc(&pl->stage_in, pl->user_in_bytes));
-      pl->stage_in_bytes = pl->user_in_bytes;
-    }
-    CUDA_OK(cudaMemcpyAsync(pl->stage_in, in, pl->user_in_bytes, cudaMemcpyHostToDevice, st));
-    dev_in = pl->stage_in;
+    dev_in = staging_area(0, pl->user_in_bytes, st);
+    CUDA_OK(cudaMemcpyAsync(dev_in, in, pl->user_in_bytes, cudaMemcpyHostToDevice, st));
+    staged_in = true;
   }
   if (pl->user_out_bytes && !device_accessible(out)) {
-    if (pl->stage_out_bytes < pl->user_out_bytes) {
-      if (pl->stage_out) cudaFree(pl->stage_out);
-      CUDA_OK(cudaMalloc(&pl->stage_out, pl->user_out_bytes));
-      pl->stage_out_bytes = pl->user_out_bytes;
-    }
-    dev_out = pl->stage_out;
+    dev_out = staging_area(1, pl->user_out_bytes, st);
     copy_back = true;
   }
   const size_t nst = s.stages.size();
   const size_t rb = pl->elem_real_bytes();
+  // where each intermediate lives: user buffers when allowed and large enough, else scratch
+  const bool destroyable = staged_in || (pl->prob.flags & F_DESTROY_INPUT) || dev_in == dev_out;
+  assign_buffers(pl, dev_in == dev_out, destroyable);
+  auto buffer_ptr = [&](int id) -> void * {
+    switch (id) {
+      case BUF_USER_IN: return dev_in;
+      case BUF_USER_OUT: return dev_out;
+      default: return pl->scratch[id - BUF_A];
+    }
+  };
   double xch_host[16] = {0};
   for (size_t i = 0; i < nst; i++) {
     const Stage &g = s.stages[i];
     StageParams sp = pl->params[i];
-    sp.in = g.in_buf == BUF_USER_IN ? dev_in : pl->scratch[g.in_buf - BUF_A];
+    sp.in = i == 0 ? dev_in : buffer_ptr(pl->assign[i - 1]);
     const bool last = i + 1 == nst;
     const bool xch = !last && g.exchange >= 0 && s.exchanges[g.exchange].nparts > 1;
     if (last) {
@@ -314,7 +417,7 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
     } else if (xch) {
       transport_stage_outputs(pl, (int)i, sp.out);
     } else {
-      char *base = static_cast<char *>(pl->scratch[g.out_buf - BUF_A]);
+      char *base = static_cast<char *>(buffer_ptr(pl->assign[i]));
       const size_t es = rb * (g.out_real ? 1 : 2);
       for (int q = 0; q < g.noseg; q++) sp.out[q] = base + (size_t)g.oseg_off[q] * es;
     }
@@ -338,7 +441,7 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
       xch_host[g.exchange % 16] += MPI_Wtime() - t0;
     }
   }
-  if (copy_back) CUDA_OK(cudaMemcpyAsync(out, pl->stage_out, pl->user_out_bytes, cudaMemcpyDeviceToHost, st));
+  if (copy_back) CUDA_OK(cudaMemcpyAsync(out, dev_out, pl->user_out_bytes, cudaMemcpyDeviceToHost, st));
   if (blocking) {
     CUDA_OK(cudaStreamSynchronize(st));
     if (pl->stage_timing) {

@@ -44,10 +44,13 @@ struct PlanBase {
   // device scratch: [0]=A, [1]=B (stage ping-pong / receive areas), [2]=W (NCCL send area)
   void *scratch[3] = {nullptr, nullptr, nullptr};
   size_t scratch_bytes = 0;
-  // host-pointer staging
-  void *stage_in = nullptr, *stage_out = nullptr;
-  size_t stage_in_bytes = 0, stage_out_bytes = 0;
+  size_t scratch_cap[3] = {0, 0, 0};
   size_t user_in_bytes = 0, user_out_bytes = 0;
+  // buffer holding what stage i hands to stage i+1 (BufId), chosen per kind of execute
+  std::vector<size_t> boundary_bytes;
+  std::vector<char> boundary_remote;
+  std::vector<int> assign;
+  int assign_key = -1;
   std::vector<StageParams> params;
   std::vector<int> use_pow2;
   std::vector<void *> tables;     // device twiddle tables owned by the plan

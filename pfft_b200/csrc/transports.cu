@@ -181,7 +181,7 @@ void transport_stage_outputs(PlanBase *pl, int i, void **out) {
   const Stage &g = pl->sched.stages[i];
   const Exchange &x = pl->sched.exchanges[g.exchange];
   const size_t es = pl->elem_real_bytes() * (g.out_real ? 1 : 2);
-  const int b = g.out_buf - BUF_A;
+  const int b = pl->assign[i] - BUF_A;
   for (int q = 0; q < x.nparts; q++) {
     if (q == x.me) {
       out[q] = static_cast<char *>(pl->scratch[b]) + (size_t)x.me * x.recv_cnt * es;
@@ -214,7 +214,7 @@ void transport_after_stage(PlanBase *pl, int i) {
   NcclApi &api = nccl();
   ncclComm_t comm = static_cast<ncclComm_t>(pl->nccl_comm);
   const size_t es = pl->elem_real_bytes() * (g.out_real ? 1 : 2);
-  const int b = g.out_buf - BUF_A;
+  const int b = pl->assign[i] - BUF_A;
   char *recv_base = static_cast<char *>(pl->scratch[b]);
   char *send_base = static_cast<char *>(pl->scratch[2]);
   api.GroupStart();
