@@ -23,6 +23,7 @@
 // Reference counterpart: FFTW guru64 plan + FFTW rank-0 copy plan per stage
 // (kernel/sertrafo.c:489-554,604-646), i.e. two passes over memory; here it is one.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -229,7 +230,7 @@ __device__ __forceinline__ void cp_async_zfill(unsigned dst_smem, const void *sr
 // distribution -> every address is  base(thread, tile) + table[e]  with the table in the
 // constant bank.  Otherwise the general (integer-division) addressing is used.
 template <typename T, int N, int E, int MAXT, bool FAST>
-__global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_kernel(const __grid_constant__ StageParams sp) {
+__global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel(const __grid_constant__ StageParams sp) {
   using P = Passes<N, E>;
   using V = typename C2<T>::type;
   constexpr int THREADS = N / E;
@@ -422,14 +423,12 @@ __global__ void __launch_bounds__(MAXT, (sizeof(T) == 8 ? 2 : 1)) stage_pow2_ker
   }
 }
 
-template <typename T>
-constexpr int max_block() { return sizeof(T) == 8 ? 256 : 512; }
-
-// (N, E) pairs compiled in; E = points per thread
-template <typename T, int N, int E>
-cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
+// (N, E) pairs compiled in; E = points per thread.  Two block-size classes per pair:
+// <= 256 threads (two CTAs per SM) and <= 512 threads (one CTA per SM, twice the lines per
+// tile, i.e. twice as long contiguous runs on a strided side).
+template <typename T, int N, int E, int MAXT>
+cudaError_t launch_block_class(StageParams &sp, cudaStream_t stream) {
   constexpr int THREADS = N / E;
-  constexpr int MAXT = max_block<T>();
   const int tl = sp.tl;
   const int skew = tl <= 8 ? 8 / tl : 0;
   using P = Passes<N, E>;
@@ -457,6 +456,13 @@ cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+template <typename T, int N, int E>
+cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
+  constexpr int THREADS = N / E;
+  if (sp.tl * THREADS <= 256) return launch_block_class<T, N, E, (THREADS > 256 ? THREADS : 256)>(sp, stream);
+  return launch_block_class<T, N, E, (THREADS > 512 ? THREADS : 512)>(sp, stream);
+}
+
 constexpr int points_per_thread(int n) {
   // three passes at most: 64 -> 8*8, 128 -> 8*8*2, 256 -> 16*16, 512 -> 8*8*8, 1024 -> 16*16*4, ...
   return (n == 64 || n == 128 || n == 512) ? 8 : 16;
@@ -481,10 +487,22 @@ bool pow2_supported(const Stage &g, int L) {
 
 template <typename T>
 int pow2_pick_tile(const Stage &g, int L) {
-  // as many lines as fit the block: a strided side then moves tl * sizeof(complex)
-  // contiguous bytes per point (64 B for fp64 / N = 1024)
+  // Lines per tile.  Default: fill a 256-thread block (fp64) / 512-thread block (fp32): two
+  // resident CTAs per SM in fp64, and a strided side then moves tl * sizeof(complex) = 64
+  // contiguous bytes per point at N = 1024.  PFFT_B200_TL overrides (experiments).
   const int threads = L / points_per_thread(L);
-  int tl = max_block<T>() / threads;
+  int block = sizeof(T) == 8 ? 256 : 512;
+  static const int forced = [] {
+    const char *e = getenv("PFFT_B200_TL");
+    return e ? atoi(e) : 0;
+  }();
+  const bool strided = g.istride != 1 || g.ostride != 1;
+  // measured on B200 (1024^3 fp64): 128-byte runs on the strided side beat two resident CTAs
+  // (8.4 vs 10.5 ms per pass; 6.8 vs 10.5 ms when half of the stores cross NVLink)
+  if (strided && sizeof(T) == 8) block = 512;
+  int tl = block / threads;
+  if (forced > 0 && strided) tl = forced;
+  while (tl * threads > 512 && tl > 1) tl /= 2;
   if (tl < 1) tl = 1;
   if (g.tile_dim < 0) tl = 1;
   else if ((INT)tl > g.batch[g.tile_dim].extent) {
