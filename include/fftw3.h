@@ -45,6 +45,23 @@ typedef float fftwf_complex[2];
 typedef long double fftwl_complex[2];
 #endif
 
+/* FFTW's allocator names, used directly by a few PFFT programs
+ * (e.g. /root/reference/tests/simple_check_ousam_r2r.c): same memory as pfft_malloc. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+void *fftw_malloc(size_t n);
+double *fftw_alloc_real(size_t n);
+fftw_complex *fftw_alloc_complex(size_t n);
+void fftw_free(void *p);
+void *fftwf_malloc(size_t n);
+float *fftwf_alloc_real(size_t n);
+fftwf_complex *fftwf_alloc_complex(size_t n);
+void fftwf_free(void *p);
+#ifdef __cplusplus
+}
+#endif
+
 #define FFTW_CONCAT(prefix, name) prefix##name
 #define FFTW_MANGLE_DOUBLE(name) FFTW_CONCAT(fftw_, name)
 #define FFTW_MANGLE_FLOAT(name) FFTW_CONCAT(fftwf_, name)

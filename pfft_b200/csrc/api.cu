@@ -556,6 +556,18 @@ void *managed_alloc(size_t bytes) {
 PFFT_B200_DEFINE_API(PFFT_NAME_D, double, PREC_F64)
 PFFT_B200_DEFINE_API(PFFT_NAME_F, float, PREC_F32)
 
+// ---- FFTW allocator names (include/fftw3.h): same managed memory as pfft_malloc -------------
+extern "C" {
+void *fftw_malloc(size_t n) { return managed_alloc(n); }
+double *fftw_alloc_real(size_t n) { return static_cast<double *>(managed_alloc(n * sizeof(double))); }
+void *fftw_alloc_complex(size_t n) { return managed_alloc(n * 2 * sizeof(double)); }
+void fftw_free(void *p) { if (p) { cudaDeviceSynchronize(); cudaFree(p); } }
+void *fftwf_malloc(size_t n) { return managed_alloc(n); }
+float *fftwf_alloc_real(size_t n) { return static_cast<float *>(managed_alloc(n * sizeof(float))); }
+void *fftwf_alloc_complex(size_t n) { return managed_alloc(n * 2 * sizeof(float)); }
+void fftwf_free(void *p) { if (p) { cudaDeviceSynchronize(); cudaFree(p); } }
+}
+
 // ---- extensions -------------------------------------------------------------------------
 namespace pfb { void set_default_transport(int t); }
 
