@@ -37,7 +37,7 @@ for name in $LIST2D $LIST3D; do
   [ -f "$src" ] || continue
   if gcc -std=gnu99 -O1 -w -I"$ROOT/include" "$src" -o "$OUT/$name" \
        -L"$ROOT/pfft_b200/lib" -lpfft_b200 -lm -Wl,-rpath,'$ORIGIN/../../../pfft_b200/lib' >>"$OUT/BUILD_LOG" 2>&1; then
-    if echo " $LIST3D " | grep -q " $name "; then echo "$name" >> "$OUT/LIST_3D"; else echo "$name" >> "$OUT/LIST_2D"; fi
+    if echo " $(echo $LIST3D) " | grep -q " $name "; then echo "$name" >> "$OUT/LIST_3D"; else echo "$name" >> "$OUT/LIST_2D"; fi
   else
     echo "SKIPPED (does not compile): $name" >> "$OUT/BUILD_LOG"
   fi

@@ -2,7 +2,7 @@
 include/pfft.h (tests/c/build_ref_tests.sh -> oracle/_ref/bin/, built in the container that
 has /root/reference), run with `pfftrun -np 4` (2-D meshes) / `-np 8` (3-D meshes) on one
 GPU.  Acceptance rule = the reference's: every printed `maxerror` below 1e-12
-(tests/run_checks.sh:75); 1e-4 for the single-precision program."""
+(tests/run_checks.sh:75); 1e-3 absolute for the single-precision program (not in run_checks.sh)."""
 import os
 import re
 import subprocess
@@ -34,7 +34,8 @@ def test_reference_program(built_lib, name, np_):
     assert p.returncode == 0, (p.returncode, p.stdout[-1500:], p.stderr[-1500:])
     errs = [float(x) for x in re.findall(r"maxerror = ([^;]*);", p.stdout)]
     assert errs, p.stdout[-1500:]
-    tol = 1e-4 if "float" in name else 1e-12
+    # the float program compares values up to 1500 in absolute terms: 1e-3 abs = 7e-7 relative
+    tol = 1e-3 if "float" in name else 1e-12
     assert max(errs) < tol, (errs, p.stdout[-800:])
 
 
