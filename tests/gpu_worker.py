@@ -97,12 +97,44 @@ def check_case(case, results):
     return err / scale
 
 
+def run_gc_case(case, comm):
+    """Ghost cells: exchange, snapshot, reduce.  Returns both snapshots (flat)."""
+    import ctypes as C
+    n, gb, ga = case["n"], case["gc_below"], case["gc_above"]
+    cplx = case.get("complex", True)
+    dtype = np.complex128 if cplx else np.float64
+    _, lni, lis, _, _ = pf.local_size("c2c", n, comm, 0)
+    L = pf.lib()
+    V = pf.INT * 3
+    ngc, gcs = V(), V()
+    L.pfft_local_size_gc_3d.restype = pf.INT
+    mem = L.pfft_local_size_gc_3d(V(*lni), V(*lis), V(*gb), V(*ga), ngc, gcs)
+    ngc, gcs = list(ngc), list(gcs)
+    buf = pf.ManagedArray(max(mem, int(np.prod(lni)), 1), dtype)
+    rng = np.random.default_rng(5)
+    xg = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    mine = xg[tuple(slice(lis[t], lis[t] + lni[t]) for t in range(3))].astype(dtype)
+    buf.array[:mine.size] = mine.reshape(-1)
+    fn = L.pfft_plan_cgc_3d if cplx else L.pfft_plan_rgc_3d
+    fn.restype = C.c_void_p
+    plan = fn(V(*n), V(*gb), V(*ga), C.c_void_p(buf.ptr), comm.handle, C.c_uint(case.get("gc_flags", 0)))
+    if not plan:
+        return dict(error="plan is NULL: " + pf.last_error())
+    L.pfft_exchange(C.c_void_p(plan))
+    exchanged = np.array(buf.array[:int(np.prod(ngc))], copy=True)
+    L.pfft_reduce(C.c_void_p(plan))
+    reduced = np.array(buf.array[:int(np.prod(ngc))], copy=True)
+    L.pfft_destroy_gcplan(C.c_void_p(plan))
+    buf.free()
+    return dict(error="", local_n=lni, local_start=lis, ngc=ngc, gc_start=gcs, out=np.concatenate([exchanged, reduced]))
+
+
 def main():
     case = json.load(open(sys.argv[1]))
     outdir = sys.argv[2]
     pf.init()
     comm = pf.create_procmesh(case["np"])
-    res = run_case(case, comm)
+    res = run_gc_case(case, comm) if case["kind"] == "gc" else run_case(case, comm)
     rank = comm.rank
     if res["error"]:
         json.dump(dict(error=res["error"]), open(os.path.join(outdir, "rank%d.json" % rank), "w"))

@@ -185,3 +185,52 @@ def test_linearity_and_parseval_at_size(world):
     pars = abs((X.norm() ** 2 / N - x.norm() ** 2) / x.norm() ** 2)
     plan.destroy(); comm.free()
     assert lin.item() < 1e-13 and pars.item() < 1e-12
+
+
+GC_CASES = [
+    dict(kind="gc", n=[8, 8, 8], np=[2, 2], gc_below=[0, 0, 0], gc_above=[4, 0, 0]),        # the reference test's halo
+    dict(kind="gc", n=[8, 8, 8], np=[2, 2], gc_below=[2, 2, 0], gc_above=[3, 3, 0]),
+    dict(kind="gc", n=[9, 7, 5], np=[2, 2], gc_below=[1, 2, 1], gc_above=[2, 1, 2]),        # ragged, halo in dim 2
+    dict(kind="gc", n=[8, 6, 4], np=[4, 1], gc_below=[3, 0, 0], gc_above=[5, 0, 0]),        # halo wider than a block
+    dict(kind="gc", n=[8, 8, 8], np=[2, 2], gc_below=[1, 1, 0], gc_above=[1, 1, 0], complex=False),
+    dict(kind="gc", n=[8, 8, 8], np=[1, 1], gc_below=[2, 0, 1], gc_above=[1, 3, 0]),
+]
+
+
+@pytest.mark.parametrize("case", GC_CASES, ids=lambda c: "gc-%s-np%s-b%s-a%s" % (
+    "x".join(map(str, c["n"])), "x".join(map(str, c["np"])), "".join(map(str, c["gc_below"])), "".join(map(str, c["gc_above"]))))
+def test_ghost_cells_match_oracle(built_lib, case):
+    """pfft_exchange / pfft_reduce against the oracle's net-effect definition."""
+    import gpu_worker
+    P = int(np.prod(case["np"]))
+    with tempfile.TemporaryDirectory() as td:
+        json.dump(case, open(os.path.join(td, "case.json"), "w"))
+        cmd = [os.path.join(ROOT, "pfft_b200", "bin", "pfftrun"), "-np", str(P), "-timeout", "120",
+               sys.executable, os.path.join(ROOT, "tests", "gpu_worker.py"), os.path.join(td, "case.json"), td]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
+        assert p.returncode == 0, (p.stdout[-2000:], p.stderr[-2000:])
+        res = []
+        for rk in range(P):
+            meta = json.load(open(os.path.join(td, "rank%d.json" % rk)))
+            assert meta.get("error", "") == "", meta["error"]
+            meta["out"] = np.load(os.path.join(td, "rank%d.npy" % rk))
+            res.append(meta)
+    n, gb, ga = case["n"], case["gc_below"], case["gc_above"]
+    cplx = case.get("complex", True)
+    rng = np.random.default_rng(5)
+    xg = rng.standard_normal(n) + (1j * rng.standard_normal(n) if cplx else 0)
+    blocks = []
+    for r in res:
+        tot = int(np.prod(r["ngc"]))
+        ex = r["out"][:tot].reshape(r["ngc"])
+        want = po.gc_exchange_block(xg, n, r["local_n"], r["local_start"], gb, ga)
+        assert np.array_equal(ex, want), "exchange must be an exact copy"
+        blocks.append((ex, r["local_n"], r["local_start"], gb, ga))
+    summed = po.gc_reduce_global(n, blocks)
+    for r in res:
+        tot = int(np.prod(r["ngc"]))
+        cnt = int(np.prod(r["local_n"]))
+        red = r["out"][tot:tot + cnt].reshape(r["local_n"])
+        sl = tuple(slice(r["local_start"][t], r["local_start"][t] + r["local_n"][t]) for t in range(3))
+        assert np.allclose(red, summed[sl], rtol=1e-14, atol=1e-14)
+        assert np.all(r["out"][tot + cnt:2 * tot] == 0), "tail must be zeroed after reduce"
