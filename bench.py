@@ -208,15 +208,42 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     local_elems = float(np.prod(n)) / world
-    alg_bytes = 2 * 16 * local_elems
-    all_stage = [x for run in stage_ms_f + stage_ms_b for x in run]
-    avg_stage_ms = sum(all_stage) / max(1, len(all_stage))
-    achieved = alg_bytes / (avg_stage_ms * 1e-3) / 1e9 if avg_stage_ms > 0 else 0.0
+    alg_pass = 2 * 16 * local_elems            # one read + one write of the local array (SURVEY.md 8d)
     desc = fwd.describe()
+
+    def launches_of(plan, runs):
+        """[(kernel name, mean ms, algorithmic bytes)] of one transform: a plane-fused pair is ONE launch
+        that transforms two dimensions (4 * 16 B * local elements), its intermediate staying in L2."""
+        d = plan.describe()
+        mean = [sum(r[i] for r in runs) / len(runs) for i in range(len(runs[0]))]
+        fi = d.get("fused_pair", -1) if d.get("fused_active", 0) else -1
+        out, i = [], 0
+        while i < len(mean):
+            if i == fi:
+                out.append(("fused_pair_kernel", mean[i] + mean[i + 1], 2 * alg_pass))
+                i += 2
+            else:
+                out.append(("stage_%s_kernel" % d["kernels"][i], mean[i], alg_pass))
+                i += 1
+        return out
+
+    per_launch = launches_of(fwd, stage_ms_f) + launches_of(bwd, stage_ms_b)
+    by_kernel = {}
+    for name, ms_k, b in per_launch:
+        t = by_kernel.setdefault(name, [0.0, 0.0, 0])
+        t[0] += ms_k
+        t[1] += b
+        t[2] += 1
+    dom = max(by_kernel, key=lambda k: by_kernel[k][0])
+    dom_ms, dom_bytes, dom_n = by_kernel[dom]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "stage kernel (%s), %d launches/step" %
-                ("/".join(sorted(set(desc["kernels"]))), launches // max(1, args.steps)),
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_stage_ms,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "%s, %d of the %d launches per step" % (dom, dom_n, launches // max(1, args.steps)),
+                "algorithmic_bytes_per_launch": dom_bytes / dom_n, "avg_launch_ms": dom_ms / dom_n,
+                "all_kernels": {k: {"launches_per_step": v[2], "ms_per_step": v[0],
+                                    "achieved_gbs": v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0}
+                                for k, v in by_kernel.items()},
                 "stage_ms_forward": [sum(r[i] for r in stage_ms_f) / len(stage_ms_f) for i in range(len(stage_ms_f[0]))],
                 "stage_ms_backward": [sum(r[i] for r in stage_ms_b) / len(stage_ms_b) for i in range(len(stage_ms_b[0]))]}
     prof = os.path.join(ROOT, "profiles", "traffic.json")

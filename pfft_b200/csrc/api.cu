@@ -630,7 +630,11 @@ size_t pfftb200_plan_describe(const void *plan, char *buf, size_t buflen) {
   }
   k += "],\"tile_lines\":[";
   for (size_t i = 0; i < pl->params.size(); i++) k += (i ? "," : "") + std::to_string(pl->params[i].tl);
-  k += "],\"transport\":\"";
+  k += "],\"fused_pair\":" + std::to_string(pl->fuse.possible ? pl->fuse.first : -1);
+  k += ",\"fused_active\":" + std::to_string(pl->fuse.active ? 1 : 0);
+  k += ",\"fused_ring_bytes\":" + std::to_string(pl->fuse.possible ? pl->fuse.ring_bytes : 0);
+  k += ",\"fused_tile_lines\":" + std::to_string(pl->fuse.possible ? pl->fuse.a.tl : 0);
+  k += ",\"transport\":\"";
   k += pl->transport == TR_NCCL ? "nccl" : "p2p";
   k += "\"}";
   j = j.substr(0, j.size() - 1) + k;

@@ -112,7 +112,7 @@ struct Stage {
   INT in_elems = 0, out_elems = 0;   // footprint in elements (for buffer sizing / roofline bytes)
 };
 
-enum BufId : int { BUF_USER_IN = 0, BUF_USER_OUT = 1, BUF_A = 2, BUF_B = 3 };
+enum BufId : int { BUF_USER_IN = 0, BUF_USER_OUT = 1, BUF_A = 2, BUF_B = 3, BUF_RING = 4 };
 
 // All-to-all over one mesh dimension. Chunk `p` of the producing stage goes to member
 // `p` of that mesh dimension's communicator and lands at recv_off[me] elements inside

@@ -226,10 +226,18 @@ __device__ __forceinline__ void cp_async_zfill(unsigned dst_smem, const void *sr
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
 }
 
+template <int BYTES>
+__device__ __forceinline__ void cp_async_plain(unsigned dst_smem, const void *src) {
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
 // FAST: no pruning, no index-shift modulation, chunk boundaries aligned with the thread
 // distribution -> every address is  base(thread, tile) + table[e]  with the table in the
 // constant bank.  Otherwise the general (integer-division) addressing is used.
-template <typename T, int N, int E, int MAXT, bool FAST>
+// DIR: 1 forward, 2 backward (the re/im swap is then pure register naming), 0 decided at run time.
+// INLM: the input is known to be line-contiguous (load mapping fixed at compile time).
+template <typename T, int N, int E, int MAXT, bool FAST, int DIR, bool INLM>
 __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel(const __grid_constant__ StageParams sp) {
   using P = Passes<N, E>;
   using V = typename C2<T>::type;
@@ -253,13 +261,23 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   const cx<T> *tw3 = tw_s + TW2;
   __syncthreads();
   // load mapping: along the line when the input is line-contiguous, else tile-minor
-  const bool in_line_major = sp.istride == 1;
+  const bool in_line_major = INLM ? true : sp.istride == 1;
   const bool out_line_major = sp.ostride == 1;
   const int t_in = in_line_major ? tid % THREADS : tid / tl;
   const int tt_in = in_line_major ? tid / THREADS : tid % tl;
   const int t_out = out_line_major ? tid % THREADS : tid / tl;
   const int tt_out = out_line_major ? tid / THREADS : tid % tl;
-  const bool backward = sp.sign > 0;
+  const bool backward = DIR == 0 ? sp.sign > 0 : DIR == 2;
+  // Barriers between passes: while a line is handled by whole warps of its own (line-major
+  // mapping), only those warps need to meet -- named barrier 1 + line -- so the lines of a tile
+  // drift apart and their load / butterfly / exchange phases overlap.  Where the store mapping is
+  // tile-minor (strided side), the last exchange mixes lines and needs the CTA-wide barrier.
+  const bool lbar_in = sp.line_bars && in_line_major && (THREADS % 32 == 0);
+  const bool lbar_out = lbar_in && out_line_major && sp.line_bars != 2;   // 2: experiment (CTA-wide around the last exchange)
+  auto sync_lines = [&](bool per_line) {
+    if (per_line) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_in), "n"(THREADS) : "memory");
+    else __syncthreads();
+  };
 
   // tile bookkeeping in 32 bits (the host refuses the fast kernels beyond 2^31 tiles)
   const unsigned ntiles = (unsigned)sp.ntiles;
@@ -299,11 +317,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   auto prefetch = [&](long long ibase, int tvalid) {
     const bool live = tt_in < tvalid;
     if (FAST) {
+      // (lines beyond a ragged tile are never stored: whatever their buffers hold is fine)
       const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is + (long long)t_in * sp.istride;
+      if (live) {
 #pragma unroll
-      for (int e = 0; e < E; e++)
-        cp_async_zfill<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)),
-                                      live ? (const void *)(in + sp.in_off[e]) : sp.in, live);
+        for (int e = 0; e < E; e++)
+          cp_async_plain<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)), in + sp.in_off[e]);
+      }
     } else {
       const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
       const bool seg_in = sp.iseg_stride != 0;
@@ -339,7 +359,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
     cx<T> x[E];
     asm volatile("cp.async.wait_all;" ::: "memory");
     {
-      const bool cj = sp.conj_in != 0;
+      const bool cj = !FAST && sp.conj_in != 0;   // (the host keeps conjugating stages off the FAST path)
 #pragma unroll
       for (int e = 0; e < E; e++) {
         const cx<T> r = my_line_in[phys(t_in + e * THREADS)];
@@ -351,28 +371,28 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
         x[e].y = backward ? re : im;
       }
     }
-    __syncthreads();   // all inputs are in registers: the buffer may be overwritten by pass 1
+    sync_lines(lbar_in);   // all inputs are in registers: the buffer may be overwritten by pass 1
 
     // ---- passes
     cx<T> *line_w = my_line_in;    // exchange buffers are addressed per line
     pass<T, N, E, P::R1, 1, false>(x, t_in, nullptr, line_w);
-    __syncthreads();
     if (P::NPASS == 3) {
+      sync_lines(lbar_in);
       {
         const cx<T> *line_r = my_line_in;
 #pragma unroll
         for (int e = 0; e < E; e++) x[e] = line_r[phys(t_in + e * THREADS)];
       }
-      __syncthreads();
+      sync_lines(lbar_in);
       pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw2, line_w);
-      __syncthreads();
     }
+    sync_lines(lbar_out);
     {
       const cx<T> *line_r = smem + tt_out * pitch;
 #pragma unroll
       for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
     }
-    __syncthreads();   // exchange buffer is free again: start fetching the next tile behind the last pass
+    sync_lines(lbar_out);   // exchange buffer is free again: start fetching the next tile behind the last pass
     const long long obase_cur = obase;
     const int tvalid_cur = tvalid;
     {
@@ -387,7 +407,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
 
     // ---- store the kept outputs
     if (tt_out < tvalid_cur) {
-      const bool cj = sp.conj_out != 0;
+      const bool cj = !FAST && sp.conj_out != 0;
       if (FAST) {
         const long long thread_off = obase_cur + (long long)tt_out * t_os + (long long)t_out * sp.ostride;
 #pragma unroll
@@ -395,7 +415,6 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
           V raw;
           raw.x = backward ? x[e].y : x[e].x;
           raw.y = backward ? x[e].x : x[e].y;
-          if (cj) raw.y = -raw.y;
           cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[sp.out_seg[e]]) + thread_off + sp.out_off[e];
           *reinterpret_cast<V *>(out) = raw;
         }
@@ -423,6 +442,359 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   }
 }
 
+// ---- plane-fused pair ------------------------------------------------------------------
+// Two consecutive stages A, B of one rank (no exchange in between) share a batch dimension
+// that neither transforms: the "plane" dimension.  Stage B's lines of plane p need exactly
+// stage A's lines of plane p, so the pair is run as ONE persistent kernel that walks the
+// planes in order -- tiles of A(p) followed by tiles of B(p - delta) -- and hands the
+// intermediate through a small ring of plane slots that never leaves the 126 MB L2:
+// A's outputs are written with an evict-last policy, B reads them back from L2, and only A's
+// reads and B's writes (both contiguous lines, evict-first) touch HBM.  A pair therefore costs
+// one read + one write of the local array instead of two of each.  Ordering is done with
+// per-plane completion counters in global memory (release increments per warp, acquire polls);
+// because every CTA takes its items in increasing order and an item only depends on items far
+// behind it, the minimum unfinished item can always run: no deadlock as long as all CTAs are
+// resident (grid = SMs x occupancy).
+// Reference counterpart: two FFTW plans + copy plans with the whole array between them
+// (kernel/partrafo-transposed.c:224-285); nothing like it exists there.
+// The counters are polled with relaxed loads: everything read behind a successful poll is
+// fetched with cp.async.cg, i.e. straight from L2, after the branch that depends on the poll.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned *p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill_hint(unsigned dst_smem, const void *src, bool ok, unsigned long long pol) {
+  const int n = ok ? BYTES : 0;
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(n), "l"(pol) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2, %3;" ::"r"(dst_smem), "l"(src), "r"(n), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(double2 *p, double2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float2 *p, float2 v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+// x / d for the runtime constant d behind (m, s1, s2) (round-up method, exact for 32-bit x)
+__device__ __forceinline__ unsigned fast_div(unsigned x, unsigned m, unsigned s1, unsigned s2) {
+  const unsigned t = __umulhi(m, x);
+  return (t + ((x - t) >> s1)) >> s2;
+}
+
+// FUSED == false: the same body runs ONE stage (spA) over a static tile sequence -- this is the
+// fast path of every power-of-two stage with contiguous input lines.
+template <typename T, int N, int E, int MAXT, bool BWD, bool FUSED>
+__global__ void __launch_bounds__(MAXT, (MAXT <= 128 ? 4 : (MAXT <= 256 ? 2 : 1)))
+fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant__ StageParams spB,
+                  const __grid_constant__ FusePlanes fp) {
+  using P = Passes<N, E>;
+  using V = typename C2<T>::type;
+  constexpr int THREADS = N / E;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
+  const int tl = spA.tl;
+  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int pitch = N + (N >> 4) + skew;
+  const int tid = threadIdx.x;
+  constexpr int TW2 = (P::R2 - 1) * P::R1;
+  constexpr int TW3 = P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0;
+  cx<T> *tw_s = smem + (size_t)tl * pitch;
+  {
+    const cx<T> *g2 = reinterpret_cast<const cx<T> *>(spA.tw2);
+    for (int i = tid; i < TW2 + TW3; i += blockDim.x) tw_s[i] = g2[i];
+  }
+  const cx<T> *tw2 = tw_s;
+  const cx<T> *tw3 = tw_s + TW2;
+  __syncthreads();
+  unsigned long long pol_first, pol_last;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_first));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
+
+  // both stages read contiguous lines: load / butterfly mapping is line-major throughout
+  const int t_in = tid % THREADS, tt_in = tid / THREADS;
+  constexpr bool backward = BWD;
+  const bool per_line = (THREADS % 32 == 0) && tl <= 15;
+  cx<T> *const my_line_in = smem + tt_in * pitch;
+  const unsigned my_line_in_s = (unsigned)__cvta_generic_to_shared(my_line_in);
+  auto sync_lines = [&](bool pl) {
+    if (pl) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_in), "n"(THREADS) : "memory");
+    else __syncthreads();
+  };
+
+  const unsigned per_round = (unsigned)(fp.t1 + fp.t2);
+  const unsigned nitems = FUSED ? per_round * (unsigned)fp.planes : (unsigned)spA.ntiles;
+  const unsigned n_head = (unsigned)fp.delta * (unsigned)fp.t1;                  // rounds with first-stage tiles only
+  const unsigned n_mid = (unsigned)(fp.planes - fp.delta) * per_round;
+  // item -> (stage, plane, tile inside the plane).  Items are handed out in this order by a
+  // ticket counter, so all CTAs advance together and what an item depends on (two rounds
+  // back) is practically always complete.
+  auto decode = [&](unsigned item, int &which, unsigned &w, int &plane) {
+    if (!FUSED) {
+      which = 0;
+      plane = 0;
+      w = item;
+    } else if (item < n_head) {
+      which = 0;
+      plane = (int)(item / (unsigned)fp.t1);
+      w = item - (unsigned)plane * (unsigned)fp.t1;
+    } else if (item < n_head + n_mid) {
+      const unsigned j = item - n_head;
+      const unsigned rnd = fast_div(j, fp.div_m, fp.div_s1, fp.div_s2);
+      w = j - rnd * per_round;
+      if (w < (unsigned)fp.t1) {
+        which = 0;
+        plane = (int)rnd + fp.delta;
+      } else {
+        which = 1;
+        w -= (unsigned)fp.t1;
+        plane = (int)rnd;
+      }
+    } else {
+      const unsigned j = item - n_head - n_mid;
+      which = 1;
+      const unsigned q = j / (unsigned)fp.t2;
+      plane = fp.planes - fp.delta + (int)q;
+      w = j - q * (unsigned)fp.t2;
+    }
+  };
+  auto flag_of = [&](int which, int plane) -> const unsigned * {
+    if (which) return fp.done + plane;
+    return fp.done + fp.planes + (plane >= fp.ring ? plane - fp.ring : 0);
+  };
+  auto flag_ok = [&](int which, int plane, unsigned v) -> bool {
+    if (!FUSED) return true;
+    if (which) return v >= fp.target1;
+    return plane < fp.ring || v >= fp.target2;
+  };
+  auto locate = [&](const StageParams &sp, int plane, unsigned w, long long &ibase, long long &obase, int &tvalid) {
+    unsigned rest = w;
+    ibase = 0;
+    obase = 0;
+    tvalid = 1;
+    if (sp.tile_dim >= 0) {
+      unsigned chunk = rest;
+      if (!FUSED || sp.nbatch > 2) {
+        const unsigned along = (unsigned)sp.tiles_along;
+        chunk = rest % along;
+        rest /= along;
+      }
+      const long long first = (long long)chunk * tl;
+      const long long left = sp.bext[sp.tile_dim] - first;
+      tvalid = left < tl ? (int)left : tl;
+      ibase = first * sp.bis[sp.tile_dim];
+      obase = first * sp.bos[sp.tile_dim];
+    }
+    if (!FUSED || sp.nbatch > 2) {
+#pragma unroll
+      for (int k = kMaxBatch - 1; k >= (FUSED ? 1 : 0); k--) {
+        if (k >= sp.nbatch || k == sp.tile_dim) continue;
+        const unsigned ext = (unsigned)sp.bext[k];
+        const unsigned c = rest % ext;
+        rest /= ext;
+        ibase += (long long)c * sp.bis[k];
+        obase += (long long)c * sp.bos[k];
+      }
+    }
+    if (FUSED) {
+      // batch dimension 0 is the plane: the ring side wraps around
+      const unsigned pi = sp.ring_in ? (unsigned)plane % (unsigned)sp.ring_in : (unsigned)plane;
+      const unsigned po = sp.ring_out ? (unsigned)plane % (unsigned)sp.ring_out : (unsigned)plane;
+      ibase += (long long)pi * sp.bis[0];
+      obase += (long long)po * sp.bos[0];
+    }
+  };
+  auto prefetch = [&](const StageParams &sp, int which, long long ibase, int tvalid) {
+    const long long t_is = sp.tile_dim >= 0 ? sp.bis[sp.tile_dim] : 0;
+    const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is + (long long)t_in * sp.istride;
+    const unsigned long long pol = which ? pol_last : pol_first;
+    if (tt_in < tvalid) {
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        const unsigned dst = my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>));
+        if (FUSED) cp_async_zfill_hint<sizeof(cx<T>)>(dst, in + sp.in_off[e], true, pol);
+        else cp_async_plain<sizeof(cx<T>)>(dst, in + sp.in_off[e]);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // completion of a tile is published one tile late, when its stores have long drained and the
+  // release costs nothing; `sig` < 0: nothing pending
+  int sig = -1;
+  auto publish = [&]() {
+    if (FUSED && sig >= 0) {
+      __syncwarp();
+      if ((tid & 31) == 0) red_release_add(fp.done + sig, 1u);
+      sig = -1;
+    }
+  };
+
+  __shared__ unsigned next_item_s[2];
+  int parity = 0;
+  unsigned *const ticket = fp.done + 2 * fp.planes;
+  int which = 0, plane = 0;
+  unsigned w = 0;
+  unsigned item = blockIdx.x;   // the first gridDim.x items are taken statically, tickets continue from there
+  long long ibase = 0, obase = 0;
+  int tvalid = 0;
+  if (item < nitems) {
+    decode(item, which, w, plane);
+    if (FUSED)
+      while (!flag_ok(which, plane, ld_relaxed_u32(flag_of(which, plane)))) __nanosleep(100);
+    locate(which ? spB : spA, plane, w, ibase, obase, tvalid);
+    prefetch(which ? spB : spA, which, ibase, tvalid);
+  }
+  while (item < nitems) {
+    const StageParams &sp = (FUSED && which) ? spB : spA;
+    const bool out_line_major = sp.ostride == 1;
+    const int t_out = out_line_major ? t_in : tid / tl;
+    const int tt_out = out_line_major ? tt_in : tid % tl;
+    const bool lbar_out = per_line && out_line_major;
+    // claim the next item now; the ticket travels while this tile is computed
+    unsigned claimed = 0;
+    if (FUSED && tid == 0) claimed = atomicAdd(ticket, 1u) + gridDim.x;
+    cx<T> x[E];
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const cx<T> r = my_line_in[phys(t_in + e * THREADS)];
+      x[e].x = backward ? r.y : r.x;
+      x[e].y = backward ? r.x : r.y;
+    }
+    sync_lines(per_line);
+    pass<T, N, E, P::R1, 1, false>(x, t_in, nullptr, my_line_in);
+    if (P::NPASS == 3) {
+      sync_lines(per_line);
+#pragma unroll
+      for (int e = 0; e < E; e++) x[e] = my_line_in[phys(t_in + e * THREADS)];
+      sync_lines(per_line);
+      pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw2, my_line_in);
+    }
+    sync_lines(lbar_out);
+    {
+      const cx<T> *line_r = smem + tt_out * pitch;
+#pragma unroll
+      for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
+    }
+    unsigned next;
+    if (FUSED) {
+      if (tid == 0) next_item_s[parity] = claimed;
+      __syncthreads();   // exchange buffers are free again, and everybody learns the next item
+      next = next_item_s[parity];
+      parity ^= 1;
+    } else {
+      sync_lines(lbar_out);
+      next = item + gridDim.x;
+    }
+    publish();   // the previous tile of this CTA
+    const long long obase_cur = obase;
+    const int tvalid_cur = tvalid;
+    int nwhich = 0, nplane = 0;
+    unsigned nw = 0;
+    bool fetched = false;
+    if (next < nitems) {
+      decode(next, nwhich, nw, nplane);
+      if (!FUSED || flag_ok(nwhich, nplane, ld_relaxed_u32(flag_of(nwhich, nplane)))) {
+        locate((FUSED && nwhich) ? spB : spA, nplane, nw, ibase, obase, tvalid);
+        prefetch((FUSED && nwhich) ? spB : spA, nwhich, ibase, tvalid);
+        fetched = true;
+      }
+    }
+    if (P::NPASS == 3) pass<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, true>(x, t_out, tw3, nullptr);
+    else pass<T, N, E, P::R2, P::R1, true>(x, t_out, tw2, nullptr);
+    if (tt_out < tvalid_cur) {
+      const long long t_os = sp.tile_dim >= 0 ? sp.bos[sp.tile_dim] : 0;
+      const long long thread_off = obase_cur + (long long)tt_out * t_os + (long long)t_out * sp.ostride;
+      const unsigned long long pol = which ? pol_first : pol_last;
+#pragma unroll
+      for (int e = 0; e < E; e++) {
+        V raw;
+        raw.x = backward ? x[e].y : x[e].x;
+        raw.y = backward ? x[e].x : x[e].y;
+        cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[sp.out_seg[e]]) + thread_off + sp.out_off[e];
+        if (FUSED) st_hint(reinterpret_cast<V *>(out), raw, pol);
+        else *reinterpret_cast<V *>(out) = raw;
+      }
+    }
+    if (FUSED) sig = which * fp.planes + plane;
+    if (FUSED && next < nitems && !fetched) {
+      // must wait: say first that this tile is done (whoever we wait for may be waiting for us)
+      publish();
+      while (!flag_ok(nwhich, nplane, ld_relaxed_u32(flag_of(nwhich, nplane)))) __nanosleep(100);
+      locate(nwhich ? spB : spA, nplane, nw, ibase, obase, tvalid);
+      prefetch(nwhich ? spB : spA, nwhich, ibase, tvalid);
+    }
+    item = next;
+    which = nwhich;
+    plane = nplane;
+    w = nw;
+  }
+  publish();
+}
+
+template <typename T, int N, int E, int MAXT>
+cudaError_t launch_fused_class(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream) {
+  constexpr int THREADS = N / E;
+  using P = Passes<N, E>;
+  constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
+  const int tl = a.tl;
+  const int skew = tl <= 8 ? 8 / tl : 0;
+  const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
+  auto kfwd = fused_pair_kernel<T, N, E, MAXT, false, true>;
+  auto kbwd = fused_pair_kernel<T, N, E, MAXT, true, true>;
+  auto kern = a.sign > 0 ? kbwd : kfwd;
+  static bool attr_set = false;
+  if (!attr_set) {
+    // (the kernel also has a few bytes of static shared memory)
+    cudaError_t e = cudaFuncSetAttribute(kfwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kbwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl * THREADS, smem);
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  const int warps = tl * THREADS / 32;
+  fp.target1 = (unsigned)fp.t1 * (unsigned)warps;
+  fp.target2 = (unsigned)fp.t2 * (unsigned)warps;
+  {
+    // magic numbers of x / (t1 + t2)
+    const unsigned d = (unsigned)(fp.t1 + fp.t2);
+    unsigned l = 0;
+    while ((1ull << l) < d) l++;
+    fp.div_m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    fp.div_s1 = l < 1 ? l : 1;
+    fp.div_s2 = l > 0 ? l - 1 : 0;
+  }
+  const long long nitems = (long long)(fp.t1 + fp.t2) * fp.planes;
+  if (nitems >= (1ll << 31)) return cudaErrorInvalidValue;
+  // all CTAs must be co-resident (they wait for one another)
+  const long long grid = std::min<long long>(nitems, (long long)sms * per_sm);
+  // completion counters [2][planes] and the ticket counter behind them
+  cudaError_t e = cudaMemsetAsync(fp.done, 0, sizeof(unsigned) * (2 * (size_t)fp.planes + 1), stream);
+  if (e != cudaSuccess) return e;
+  kern<<<(unsigned)grid, tl * THREADS, smem, stream>>>(a, b, fp);
+  launch_counter()++;
+  return cudaGetLastError();
+}
+
+template <typename T, int N, int E>
+cudaError_t launch_fused_variant(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream) {
+  constexpr int THREADS = N / E;
+  const int block = a.tl * THREADS;
+  if (block <= 128) return launch_fused_class<T, N, E, (THREADS > 128 ? THREADS : 128)>(a, b, fp, stream);
+  if (block <= 256) return launch_fused_class<T, N, E, (THREADS > 256 ? THREADS : 256)>(a, b, fp, stream);
+  return launch_fused_class<T, N, E, (THREADS > 512 ? THREADS : 512)>(a, b, fp, stream);
+}
+
 // (N, E) pairs compiled in; E = points per thread.  Two block-size classes per pair:
 // <= 256 threads (two CTAs per SM) and <= 512 threads (one CTA per SM, twice the lines per
 // tile, i.e. twice as long contiguous runs on a strided side).
@@ -434,14 +806,40 @@ cudaError_t launch_block_class(StageParams &sp, cudaStream_t stream) {
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
-  auto fast = stage_pow2_kernel<T, N, E, MAXT, true>;
-  auto slow = stage_pow2_kernel<T, N, E, MAXT, false>;
-  auto kern = sp.fast ? fast : slow;
+  if (sp.fast && sp.istride == 1) {
+    // contiguous input lines: the lean body shared with the plane-fused pair
+    auto kf = fused_pair_kernel<T, N, E, MAXT, false, false>;
+    auto kb = fused_pair_kernel<T, N, E, MAXT, true, false>;
+    auto k1 = sp.sign > 0 ? kb : kf;
+    static bool attr1_set = false;
+    if (!attr1_set) {
+      cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+      if (e != cudaSuccess) return e;
+      attr1_set = true;
+    }
+    int dev1 = 0, sms1 = 148, per_sm1 = 1;
+    cudaGetDevice(&dev1);
+    cudaDeviceGetAttribute(&sms1, cudaDevAttrMultiProcessorCount, dev1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm1, k1, tl * THREADS, smem);
+    if (per_sm1 < 1) per_sm1 = 1;
+    const long long grid1 = std::min<long long>(sp.ntiles, (long long)sms1 * per_sm1);
+    FusePlanes none = {};
+    k1<<<(unsigned)grid1, tl * THREADS, smem, stream>>>(sp, sp, none);
+    launch_counter()++;
+    return cudaGetLastError();
+  }
+  using K = void (*)(StageParams);
+  // [0] general (run-time direction), [1] / [2] FAST forward / backward (strided input lines here)
+  K kerns[3] = {stage_pow2_kernel<T, N, E, MAXT, false, 0, false>, stage_pow2_kernel<T, N, E, MAXT, true, 1, false>,
+                stage_pow2_kernel<T, N, E, MAXT, true, 2, false>};
+  K kern = kerns[sp.fast ? 1 + (sp.sign > 0 ? 1 : 0) : 0];
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fast, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(slow, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
+    for (K k : kerns) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   int dev = 0, sms = 148;
@@ -502,6 +900,11 @@ int pow2_pick_tile(const Stage &g, int L) {
   if (strided && sizeof(T) == 8) block = 512;
   int tl = block / threads;
   if (forced > 0 && strided) tl = forced;
+  static const int forced_c = [] {
+    const char *e = getenv("PFFT_B200_TLC");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced_c > 0 && !strided) tl = forced_c;
   while (tl * threads > 512 && tl > 1) tl /= 2;
   if (tl < 1) tl = 1;
   if (g.tile_dim < 0) tl = 1;
@@ -527,18 +930,54 @@ cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream) {
   }
 }
 
+// Threads of a block must be whole warps and at least 128 for the fused pair; lines per tile
+// are chosen for 32-byte runs on the ring side (L2 sectors), not for HBM.
+template <typename T>
+int fused_pick_tile(int L) {
+  const int threads = L / points_per_thread(L);
+  int tl = (int)(32 / (2 * sizeof(T)));
+  static const int forced = [] {
+    const char *e = getenv("PFFT_B200_FTL");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced > 0) tl = forced;
+  while (tl * threads < 128) tl *= 2;
+  while (tl * threads > 512 && tl > 1) tl /= 2;
+  return tl;
+}
+
+template <typename T>
+cudaError_t launch_fused_pow2(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream) {
+  if (a.L != b.L || a.tl != b.tl) return cudaErrorInvalidValue;
+  switch (a.L) {
+    case 64: return launch_fused_variant<T, 64, 8>(a, b, fp, stream);
+    case 128: return launch_fused_variant<T, 128, 8>(a, b, fp, stream);
+    case 256: return launch_fused_variant<T, 256, 16>(a, b, fp, stream);
+    case 512: return launch_fused_variant<T, 512, 8>(a, b, fp, stream);
+    case 1024: return launch_fused_variant<T, 1024, 16>(a, b, fp, stream);
+    case 2048: return launch_fused_variant<T, 2048, 16>(a, b, fp, stream);
+    case 4096: return launch_fused_variant<T, 4096, 16>(a, b, fp, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 // Decide whether the table-driven addressing applies and fill the tables.
 template <typename T>
 void pow2_prepare(const Stage &g, StageParams &sp) {
   const int L = sp.L;
   const int E = points_per_thread(L);
   const int threads = L / E;
-  bool fast = g.nin == L && g.zin == 0 && g.nout == L && g.zout == 0 && !g.mod_in.on && !g.mod_out.on;
+  bool fast = g.nin == L && g.zin == 0 && g.nout == L && g.zout == 0 && !g.mod_in.on && !g.mod_out.on && !g.conj_in && !g.conj_out;
   const bool seg_in = g.iseg_stride != 0 && g.iblk < g.nin;
   const bool seg_out = g.noseg > 1;
   if (seg_in && g.iblk % threads != 0) fast = false;
   if (seg_out && g.oblk % threads != 0) fast = false;
   sp.fast = fast ? 1 : 0;
+  static const int line_bars = [] {
+    const char *e = getenv("PFFT_B200_LINEBAR");
+    return e ? atoi(e) : 1;
+  }();
+  sp.line_bars = sp.tl <= 15 ? line_bars : 0;
   if (!fast) return;
   for (int e = 0; e < E; e++) {
     const long long idx = (long long)e * threads;
@@ -590,6 +1029,10 @@ template int pow2_pick_tile<float>(const Stage &, int);
 template int pow2_pick_tile<double>(const Stage &, int);
 template cudaError_t launch_stage_pow2<float>(StageParams &, cudaStream_t);
 template cudaError_t launch_stage_pow2<double>(StageParams &, cudaStream_t);
+template int fused_pick_tile<float>(int);
+template int fused_pick_tile<double>(int);
+template cudaError_t launch_fused_pow2<float>(StageParams &, StageParams &, FusePlanes &, cudaStream_t);
+template cudaError_t launch_fused_pow2<double>(StageParams &, StageParams &, FusePlanes &, cudaStream_t);
 template void pow2_prepare<float>(const Stage &, StageParams &);
 template void pow2_prepare<double>(const Stage &, StageParams &);
 

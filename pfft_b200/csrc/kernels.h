@@ -40,10 +40,23 @@ struct StageParams {
   int fac[kMaxFactors];
   // power-of-two fast path (fft_pow2.cu)
   int fast;                  // table-driven addressing applies
+  int line_bars;             // per-line named barriers between passes (else CTA-wide)
+  int ring_in, ring_out;     // fused pair: batch dimension 0 (the plane) wraps around a ring of this many slots
   const void *tw2, *tw3;     // per-pass twiddle tables [r-1][k]
   long long in_off[16];      // element offset of line index e*THREADS on input
   long long out_off[16];     // ... on output, inside chunk out_seg[e]
   int out_seg[16];
+};
+
+// Plane-fused pair of stages (fft_pow2.cu: fused_pair_kernel).
+struct FusePlanes {
+  int planes;                // extent of the plane dimension (batch index 0 of both stages)
+  int t1, t2;                // tiles per plane of the first / second stage
+  int delta;                 // the second stage runs `delta` planes behind the first
+  int ring;                  // plane slots of the intermediate ring buffer
+  unsigned target1, target2; // counter value that means "plane complete"
+  unsigned div_m, div_s1, div_s2;   // fast division by t1 + t2
+  unsigned *done;            // [2][planes] completion counters
 };
 
 // host-side helpers (fft_tables.cpp)
@@ -66,6 +79,10 @@ template <typename T>
 int pow2_pick_tile(const Stage &g, int L);
 template <typename T>
 void pow2_prepare(const Stage &g, StageParams &sp);
+template <typename T>
+int fused_pick_tile(int L);
+template <typename T>
+cudaError_t launch_fused_pow2(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream);
 void pow2_twiddle_tables(int L, const double *roots, std::vector<double> *table, size_t *off2, size_t *off3);
 
 unsigned long long &launch_counter();

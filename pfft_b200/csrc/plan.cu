@@ -184,6 +184,158 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
   return true;
 }
 
+// ---- plane-fused last pair -------------------------------------------------------------
+namespace {
+struct DimSE {
+  long long stride, extent;
+};
+// canonical form of an address set given as a sum of strided dimensions
+std::vector<DimSE> canonical(std::vector<DimSE> v) {
+  std::vector<DimSE> w;
+  for (auto &d : v)
+    if (d.extent > 1) w.push_back(d);
+  std::sort(w.begin(), w.end(), [](const DimSE &x, const DimSE &y) { return x.stride < y.stride; });
+  std::vector<DimSE> out;
+  for (auto &d : w) {
+    if (!out.empty() && out.back().stride * out.back().extent == d.stride) out.back().extent *= d.extent;
+    else out.push_back(d);
+  }
+  return out;
+}
+bool same_set(const std::vector<DimSE> &a, const std::vector<DimSE> &b) {
+  if (a.size() != b.size()) return false;
+  for (size_t i = 0; i < a.size(); i++)
+    if (a[i].stride != b[i].stride || a[i].extent != b[i].extent) return false;
+  return true;
+}
+// Make the plane (stride `ps` on the given side, `planes` of them) batch dimension 0 of sp,
+// splitting it out of a merged batch dimension if necessary.
+bool plane_first(StageParams &sp, bool out_side, long long ps, long long planes) {
+  int nb = sp.nbatch;
+  long long ext[kMaxBatch + 1], is[kMaxBatch + 1], os[kMaxBatch + 1];
+  int tile = sp.tile_dim;
+  for (int k = 0; k < nb; k++) { ext[k] = sp.bext[k]; is[k] = sp.bis[k]; os[k] = sp.bos[k]; }
+  int kp = -1;
+  for (int k = 0; k < nb; k++) {
+    const long long st = out_side ? os[k] : is[k];
+    if (st == ps && ext[k] == planes) { kp = k; break; }
+  }
+  if (kp < 0) {
+    for (int k = 0; k < nb && kp < 0; k++) {
+      const long long st = out_side ? os[k] : is[k];
+      if (st <= 0 || st >= ps || ps % st) continue;
+      const long long q = ps / st;
+      if (ext[k] % q || ext[k] / q != planes || nb + 1 > kMaxBatch) continue;
+      // split dimension k into (planes, q): insert the inner part behind it
+      for (int j = nb; j > k + 1; j--) { ext[j] = ext[j - 1]; is[j] = is[j - 1]; os[j] = os[j - 1]; }
+      ext[k + 1] = q; is[k + 1] = is[k]; os[k + 1] = os[k];
+      ext[k] = planes; is[k] *= q; os[k] *= q;
+      if (tile == k) tile = k + 1;
+      else if (tile > k) tile++;
+      nb++;
+      kp = k;
+    }
+  }
+  if (kp < 0 || kp == tile) return false;
+  // rotate kp to the front
+  const long long e0 = ext[kp], i0 = is[kp], o0 = os[kp];
+  for (int j = kp; j > 0; j--) { ext[j] = ext[j - 1]; is[j] = is[j - 1]; os[j] = os[j - 1]; }
+  ext[0] = e0; is[0] = i0; os[0] = o0;
+  if (tile >= 0 && tile < kp) tile++;
+  sp.nbatch = nb;
+  sp.tile_dim = tile;
+  for (int k = 0; k < nb; k++) { sp.bext[k] = ext[k]; sp.bis[k] = is[k]; sp.bos[k] = os[k]; }
+  return true;
+}
+}  // namespace
+
+template <typename T>
+static void setup_fused_pair(PlanBase *pl) {
+  FusedPair &f = pl->fuse;
+  f.possible = false;
+  // Opt-in (PFFT_B200_FUSE=1): measured on B200 at 1024^3 fp64 the pair costs 14.2-14.6 ms against
+  // 7.2 + 5.5 ms for the two stages run separately -- the first stage's cross-line exchange with
+  // two-line tiles and the ticket/flag traffic cost more than the halved HBM traffic returns.
+  const char *env = getenv("PFFT_B200_FUSE");
+  if (!env || atoi(env) == 0) return;
+  const Schedule &s = pl->sched;
+  const int nst = (int)s.stages.size();
+  if (nst < 2) return;
+  const int i = nst - 2;
+  const Stage &ga = s.stages[i], &gb = s.stages[i + 1];
+  if (!pl->use_pow2[i] || !pl->use_pow2[i + 1]) return;
+  StageParams a = pl->params[i], b = pl->params[i + 1];
+  if (!a.fast || !b.fast || a.L != b.L || a.sign != b.sign) return;
+  if (sizeof(T) != 8) return;   // 8-byte cp.async is L1-cached (.ca): ring data written by other SMs could be stale
+  if (ga.exchange >= 0 && s.exchanges[ga.exchange].nparts > 1) return;
+  if (a.noseg != 1 || b.noseg != 1 || a.istride != 1 || b.istride != 1) return;
+  if (a.ntiles <= 0 || b.ntiles <= 0 || a.nbatch < 1 || b.nbatch < 1) return;
+  // plane = outermost dimension of the intermediate array
+  int ka = 0;
+  for (int k = 1; k < a.nbatch; k++)
+    if (a.bos[k] > a.bos[ka]) ka = k;
+  const long long ps = a.bos[ka];
+  long long planes = a.bext[ka];
+  // everything else A writes / B reads must stay inside one plane slot
+  {
+    long long span = (long long)(a.L - 1) * a.ostride + 1;
+    for (int k = 0; k < a.nbatch; k++)
+      if (k != ka) span += (a.bext[k] - 1) * a.bos[k];
+    if (span > ps) return;
+  }
+  if (!plane_first(a, true, ps, planes)) return;
+  if (!plane_first(b, false, ps, planes)) return;
+  {
+    long long span = (long long)(b.L - 1) * b.istride + 1;
+    for (int k = 1; k < b.nbatch; k++) span += (b.bext[k] - 1) * b.bis[k];
+    if (span > ps) return;
+  }
+  const char *er = getenv("PFFT_B200_RING"), *ed = getenv("PFFT_B200_DELTA");
+  const int delta = ed ? std::max(1, atoi(ed)) : 2;
+  const int ring = er ? std::max(delta + 1, atoi(er)) : delta + 2;
+  const size_t plane_bytes = (size_t)ps * 2 * sizeof(T);
+  if (planes < 2 * ring || plane_bytes * ring > ((size_t)96 << 20)) return;
+  // tiles: short runs are fine on the ring side (it lives in L2), so small independent CTAs
+  const int tl = fused_pick_tile<T>(a.L);
+  auto retile = [&](StageParams &sp) {
+    sp.tl = tl;
+    if (sp.tile_dim < 0) return false;
+    if (sp.bext[sp.tile_dim] < tl) return false;
+    sp.tiles_along = (sp.bext[sp.tile_dim] + tl - 1) / tl;
+    long long others = 1;
+    for (int k = 0; k < sp.nbatch; k++)
+      if (k != sp.tile_dim) others *= sp.bext[k];
+    sp.ntiles = others * sp.tiles_along;
+    return sp.ntiles < (1ll << 30);
+  };
+  if (!retile(a) || !retile(b)) return;
+  a.ring_out = ring;
+  a.ring_in = 0;
+  b.ring_in = ring;
+  b.ring_out = 0;
+  f.fp.planes = (int)planes;
+  f.fp.t1 = (int)(a.ntiles / planes);
+  f.fp.t2 = (int)(b.ntiles / planes);
+  f.fp.delta = delta;
+  f.fp.ring = ring;
+  f.fp.done = nullptr;
+  // same addresses for plane p on the pair's input and output side?
+  {
+    std::vector<DimSE> in_set, out_set;
+    in_set.push_back({a.istride, a.L});
+    for (int k = 1; k < a.nbatch; k++) in_set.push_back({a.bis[k], a.bext[k]});
+    out_set.push_back({b.ostride, b.L});
+    for (int k = 1; k < b.nbatch; k++) out_set.push_back({b.bos[k], b.bext[k]});
+    f.inplace_ok = a.bis[0] == b.bos[0] && same_set(canonical(in_set), canonical(out_set));
+  }
+  f.a = a;
+  f.b = b;
+  f.first = i;
+  f.ring_bytes = plane_bytes * ring;
+  f.possible = true;
+  (void)gb;
+}
+
 PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm comm) {
   ensure_device();
   PlanBase *pl = new PlanBase;
@@ -199,6 +351,7 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
   bool ok = build_schedule(p, pid, &pl->sched);
   if (!ok) err = pl->sched.error;
   if (ok) ok = prec == PREC_F64 ? build_stage_params<double>(pl, &err) : build_stage_params<float>(pl, &err);
+  if (ok) { if (prec == PREC_F64) setup_fused_pair<double>(pl); else setup_fused_pair<float>(pl); }
   if (!all_ranks_ok(pl->comm_cart, ok)) {
     set_error(err.empty() ? "planning failed on another rank" : err);
     plan_destroy(pl);
@@ -261,6 +414,12 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
       return nullptr;
     }
   }
+  if (pl->fuse.possible) {
+    CUDA_OK(cudaMalloc(&pl->fuse.ring, pl->fuse.ring_bytes));
+    void *cnt = nullptr;
+    CUDA_OK(cudaMalloc(&cnt, sizeof(unsigned) * (2 * (size_t)pl->fuse.fp.planes + 1)));
+    pl->fuse.fp.done = static_cast<unsigned *>(cnt);
+  }
   pl->events.resize(2 * nst);
   for (auto &e : pl->events) CUDA_OK(cudaEventCreate(&e));
   pl->timer.shape(p.rnk_pm);
@@ -274,6 +433,8 @@ void plan_destroy(PlanBase *pl) {
   if (pl->stream || true) cudaStreamSynchronize(pl->stream);
   transport_teardown(pl);
   for (auto &e : pl->events) cudaEventDestroy(e);
+  if (pl->fuse.ring) cudaFree(pl->fuse.ring);
+  if (pl->fuse.fp.done) cudaFree(pl->fuse.fp.done);
   for (void *t : pl->tables) cudaFree(t);
   for (int k = 0; k < 3; k++)
     if (pl->scratch[k]) cudaFree(pl->scratch[k]);
@@ -318,13 +479,20 @@ static void *staging_area(int which, size_t bytes, cudaStream_t st) {
 static void assign_buffers(PlanBase *pl, bool inplace, bool destroyable) {
   const int key = (inplace ? 1 : 0) | (destroyable ? 2 : 0);
   if (pl->assign_key == key && !pl->assign.empty()) return;
-  const size_t nb = pl->boundary_bytes.size();
+  const size_t nb_all = pl->boundary_bytes.size();
   bool any_remote = false;
-  for (size_t i = 0; i < nb; i++) any_remote |= pl->boundary_remote[i] != 0;
+  for (size_t i = 0; i < nb_all; i++) any_remote |= pl->boundary_remote[i] != 0;
+  // the fused pair hands its intermediate through the ring; its input array must not be the
+  // array it writes unless both use the same addresses plane by plane
+  FusedPair &fu = pl->fuse;
+  fu.active = fu.possible && nb_all >= 1;
+  if (fu.active && nb_all == 1 && inplace && !fu.inplace_ok) fu.active = false;
+  const size_t nb = fu.active ? nb_all - 1 : nb_all;
   if (any_remote) {
     // peers store into these areas: every rank must pick the same ones, whatever its block sizes
-    pl->assign.resize(nb);
-    for (size_t i = 0; i < nb; i++) pl->assign[i] = (i % 2) ? BUF_B : BUF_A;
+    pl->assign.resize(nb_all);
+    for (size_t i = 0; i < nb_all; i++) pl->assign[i] = (i % 2) ? BUF_B : BUF_A;
+    if (fu.active) pl->assign[nb_all - 1] = BUF_RING;
     pl->assign_key = key;
     return;
   }
@@ -345,7 +513,7 @@ static void assign_buffers(PlanBase *pl, bool inplace, bool destroyable) {
       if (inplace && id == BUF_USER_OUT) continue;                  // same array as BUF_USER_IN
       if (id == prev) continue;
       if (inplace && prev == BUF_USER_IN && id == BUF_USER_IN) continue;
-      if (i + 1 == nb && (id == BUF_USER_OUT || (inplace && id == BUF_USER_IN))) continue;
+      if (i + 1 == nb && (id == BUF_USER_OUT || (inplace && id == BUF_USER_IN)) && !(fu.active && fu.inplace_ok)) continue;
       if (pl->boundary_remote[i] && id < BUF_A) continue;
       if (id == BUF_USER_IN && (!destroyable || pl->boundary_bytes[i] > pl->user_in_bytes)) continue;
       if (id == BUF_USER_OUT && pl->boundary_bytes[i] > pl->user_out_bytes) continue;
@@ -359,13 +527,14 @@ static void assign_buffers(PlanBase *pl, bool inplace, bool destroyable) {
     best.assign(nb, BUF_A);
     for (size_t i = 0; i < nb; i++) best[i] = (i % 2) ? BUF_B : BUF_A;
   }
+  if (fu.active) best.push_back(BUF_RING);
   pl->assign = best;
   pl->assign_key = key;
   // scratch on demand (plans with exchanges allocated theirs up front)
   for (int k = 0; k < 2; k++) {
     size_t need = 0;
     for (size_t i = 0; i < nb; i++)
-      if (best[i] == BUF_A + k) need = std::max(need, pl->boundary_bytes[i]);
+      if (best[i] == BUF_A + k) need = std::max(need, pl->boundary_bytes[i]);   // (the ring is plan-owned)
     if (need > pl->scratch_cap[k]) {
       CUDA_OK(cudaStreamSynchronize(pl->stream));
       if (pl->scratch[k]) cudaFree(pl->scratch[k]);
@@ -402,6 +571,7 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
     switch (id) {
       case BUF_USER_IN: return dev_in;
       case BUF_USER_OUT: return dev_out;
+      case BUF_RING: return pl->fuse.ring;
       default: return pl->scratch[id - BUF_A];
     }
   };
@@ -420,6 +590,24 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
       char *base = static_cast<char *>(buffer_ptr(pl->assign[i]));
       const size_t es = rb * (g.out_real ? 1 : 2);
       for (int q = 0; q < g.noseg; q++) sp.out[q] = base + (size_t)g.oseg_off[q] * es;
+    }
+    if (pl->fuse.active && (int)i == pl->fuse.first) {
+      // the last two stages as one plane-fused launch
+      StageParams a = pl->fuse.a, b = pl->fuse.b;
+      a.in = sp.in;
+      a.out[0] = pl->fuse.ring;
+      b.in = pl->fuse.ring;
+      b.out[0] = dev_out;
+      if (pl->stage_timing) cudaEventRecord(pl->events[2 * i], st);
+      cudaError_t e = pl->prec == PREC_F64 ? launch_fused_pow2<double>(a, b, pl->fuse.fp, st)
+                                            : launch_fused_pow2<float>(a, b, pl->fuse.fp, st);
+      CUDA_OK(e);
+      if (pl->stage_timing) {
+        cudaEventRecord(pl->events[2 * i + 1], st);
+        cudaEventRecord(pl->events[2 * i + 2], st);
+        cudaEventRecord(pl->events[2 * i + 3], st);
+      }
+      break;
     }
     double t0 = 0;
     if (xch) {

@@ -34,6 +34,18 @@ struct TimerData {
 
 struct PeerMap;   // transports.cu
 
+// Last two stages of a rank run as one plane-fused kernel (fft_pow2.cu: fused_pair_kernel)
+struct FusedPair {
+  bool possible = false;     // kernel-side conditions hold
+  bool active = false;       // used by the current buffer assignment
+  bool inplace_ok = false;   // plane p of the pair's input and of its output occupy the same addresses
+  int first = -1;            // index of the pair's first stage
+  StageParams a, b;          // stage parameters with the plane as batch dimension 0
+  FusePlanes fp = {};
+  void *ring = nullptr;      // intermediate: fp.ring plane slots
+  size_t ring_bytes = 0;
+};
+
 struct PlanBase {
   int prec = PREC_F64;
   Problem prob;
@@ -63,6 +75,7 @@ struct PlanBase {
   bool stage_timing = true;
   std::vector<double> last_stage_ms;
   std::vector<double> last_xch_ms;
+  FusedPair fuse;
   size_t elem_real_bytes() const { return prec == PREC_F64 ? 8 : 4; }
 };
 

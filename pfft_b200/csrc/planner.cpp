@@ -260,7 +260,7 @@ struct Builder {
       g.oblk = st.split_blk;
       INT off = 0;
       for (int q = 0; q < noseg; q++) {
-        g.oseg_cnt[q] = seg_rows[q] * Lout.stride[a];
+        g.oseg_cnt[q] = noseg == 1 ? Lout.total : seg_rows[q] * Lout.stride[a];
         g.oseg_off[q] = off;
         off += g.oseg_cnt[q];
       }
@@ -321,13 +321,24 @@ struct Builder {
 
   // intermediate layout in front of an exchange: split dim outermost, gathered dim
   // innermost (before the always-local trailing dims and the tuple)
-  Layout chunk_layout(int split, int gather, INT gather_pitch, bool real) const {
+  // `mode` 0: as above.  Boundaries without a real exchange (one rank along the mesh
+  // dimension) are free to use any order: mode 1 = [others][split][gather] keeps the dimensions
+  // that neither neighbouring stage transforms outermost ("planes"), so consecutive lines of the
+  // producing stage land within one plane (short strides) and the two stages around the
+  // boundary can be run plane by plane through L2 (plan.cu: fused pair); mode 2 = explicit
+  // order given by the caller.
+  Layout chunk_layout(int split, int gather, INT gather_pitch, bool real, int mode = 0, const int *explicit_order = nullptr) const {
     Layout L;
     int k = 0;
-    L.order[k++] = split;
-    for (int t = 0; t <= r; t++)
-      if (t != split && t != gather) L.order[k++] = t;
-    L.order[k++] = gather;
+    if (mode == 2) {
+      for (int t = 0; t <= r; t++) L.order[k++] = explicit_order[t];
+    } else {
+      if (mode == 0) L.order[k++] = split;
+      for (int t = 0; t <= r; t++)
+        if (t != split && t != gather) L.order[k++] = t;
+      if (mode == 1) L.order[k++] = split;
+      L.order[k++] = gather;
+    }
     for (int t = r + 1; t < d; t++) L.order[k++] = t;
     L.order[k++] = kTuple;
     L.nord = k;
@@ -454,7 +465,32 @@ struct Builder {
         if (Lout.real != out_real) { s.error = "internal: element type mismatch at the last stage"; return false; }
       } else if (st.xch_mesh >= 0) {
         const int m = st.xch_mesh;
-        Lout = chunk_layout(st.xch_split, st.xch_gather, st.gather_blk, out_real);
+        // local boundaries in front of / inside the last pair of stages: plane-friendly orders
+        int mode = 0;
+        int ord[kMaxDims + 1];
+        const size_t ns = steps.size();
+        const bool simple = d == r + 1 && p.howmany == 1 && ns >= 2;
+        const bool pair_local = simple && steps[ns - 2].xch_mesh >= 0 && np[steps[ns - 2].xch_mesh] == 1;
+        if (np[m] == 1 && simple) {
+          if (i + 2 == ns) {
+            mode = 1;
+          } else if (i + 3 == ns && pair_local) {
+            // input of the pair = final layout with the pair's two dimensions swapped: plane p of
+            // the pair's input then occupies exactly the addresses of plane p of the final output
+            const int x = steps[ns - 2].dim, y = steps[ns - 1].dim;
+            int k = 0;
+            for (int q = 0; q < Lfinal.nord; q++) {
+              const int t = Lfinal.order[q];
+              if (t == kTuple || t > r) continue;
+              ord[k++] = t == x ? y : (t == y ? x : t);
+            }
+            if (k == r + 1 && ord[r] == st.xch_gather) mode = 2;
+            else mode = 1;
+          } else {
+            mode = 1;
+          }
+        }
+        Lout = chunk_layout(st.xch_split, st.xch_gather, st.gather_blk, out_real, mode, ord);
         Lout.finish();
         noseg = np[m];
         for (int q = 0; q < noseg; q++) seg_rows[q] = block_extent(st.split_n, st.split_blk, q);

@@ -82,7 +82,8 @@ def run_case(case, comm, seed=0):
         if not inplace:
             ma_out.free()
     return dict(error="", local_ni=lni, local_i_start=lis, local_no=lno, local_o_start=los, out=out,
-                input_preserved=preserved, kernels=desc["kernels"], transport=desc["transport"])
+                input_preserved=preserved, kernels=desc["kernels"], transport=desc["transport"],
+                fused=desc.get("fused_active", 0))
 
 
 def check_case(case, results):

@@ -74,6 +74,18 @@ SINGLE_RANK = [
     dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=S_IN | S_OUT | T_OUT),
     dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[1, 1], flags=S_IN | S_OUT),
     dict(kind="c2c", n=[8, 6, 4], np=[1, 1], skip=[0, 1, 0]),
+    # plane-fused last pair (power-of-two lines of equal length in the last two stages)
+    dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_OUT, tag="-fused"),
+    dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
+    dict(kind="c2c", n=[128, 128, 128], np=[1, 1], flags=T_OUT, tag="-fused"),
+    dict(kind="c2c", n=[128, 128, 128], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
+    dict(kind="c2c", n=[128, 128, 128], np=[1, 1], flags=T_OUT, inplace=True, tag="-fused"),
+    dict(kind="c2c", n=[128, 128, 64], np=[1, 1], flags=T_OUT, tag="-fused"),
+    dict(kind="c2c", n=[64, 128, 128], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
+    dict(kind="c2c", n=[128, 128, 128], np=[1, 1], flags=T_OUT, precision="single", tag="-fused"),
+    dict(kind="c2c", n=[64, 512, 512], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
+    dict(kind="c2c", n=[512, 512, 32], np=[1, 1], flags=T_OUT, repeat=2, tag="-fused"),
+    dict(kind="c2c", n=[64, 64, 64, 64], np=[1, 1, 1], flags=T_OUT, tag="-fused"),
 ]
 
 
@@ -87,6 +99,8 @@ def test_single_rank_matches_oracle(world, case):
     err = gpu_worker.check_case(case, [res])
     assert err < TOL[case.get("precision", "double")], err
     assert res["input_preserved"], "out-of-place plans must not touch the input (PFFT_PRESERVE_INPUT default)"
+    if case.get("tag") == "-fused" and case.get("precision", "double") == "double" and os.environ.get("PFFT_B200_FUSE", "0") == "1":
+        assert res["fused"] == 1, "expected the plane-fused pair kernel for this case"
 
 
 MULTI_RANK = [
