@@ -113,11 +113,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--transport", default=None)
+    ap.add_argument("--mesh", default=None, help="process mesh P0xP1 (default: 1x1, 2x1, 2x2, 2x4 for 1/2/4/8 ranks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = [args.size] * 3
-    mesh = MESH.get(world, [world, 1])
+    mesh = [int(v) for v in args.mesh.split("x")] if args.mesh else MESH.get(world, [world, 1])
     config = {"workload": "%d^3 c2c fp64 forward(TRANSPOSED_OUT)+backward(TRANSPOSED_IN), mesh %dx%d" %
               (args.size, mesh[0], mesh[1]), "n": n, "mesh": mesh, "flags": "PFFT_TRANSPOSED_OUT/IN",
               "l2_policy": "arrays (>= 2 GiB per rank) far exceed the 126 MB L2; no flush needed"}
