@@ -97,6 +97,15 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constan
         }
         if (sp.conj_in) v.y = -v.y;
         if (sp.mod_in.on && sign_mod(sp.mod_in, j) < 0) { v.x = -v.x; v.y = -v.y; }
+        if (sp.op == OP_R2R) {
+          // w_j x_j exp(-i pi b jj / D), jj = position inside the logical line of n reals
+          const int jj = j + sp.zin;
+          T xr = v.x;
+          if ((jj == 0 && sp.r2r_half0) || (jj == sp.n - 1 && sp.r2r_halfn)) xr *= (T)0.5;
+          const C w = reinterpret_cast<const C *>(sp.tw_r2r)[(int)(((long long)2 * sp.r2r_b2 * jj) % (8ll * sp.r2r_D))];
+          v.x = xr * w.x;
+          v.y = xr * w.y;
+        }
         buf0[tt * L + j + sp.zin] = v;
       }
     }
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constan
     // ---- mixed-radix Stockham passes, one output per thread
     C *src = buf0, *dst = buf1;
     if (sp.op != OP_COPY) {
-      const bool backward = sp.sign > 0;
+      const bool backward = sp.op != OP_R2R && sp.sign > 0;
       int Ns = 1;
       for (int f = 0; f < sp.nfac; f++) {
         const int R = sp.fac[f];
@@ -162,6 +171,14 @@ __global__ void __launch_bounds__(256) stage_generic_kernel(const __grid_constan
         if (contiguous) { tt = e / sp.nout; kk = e - tt * sp.nout; }
         else { kk = e / tvalid; tt = e - kk * tvalid; }
         C v = src[tt * L + kk + sp.zout];
+        if (sp.op == OP_R2R) {
+          // 2 F(exp(-i pi a (k + b) / D) X_k)
+          const int k = kk + sp.zout;
+          const C w = reinterpret_cast<const C *>(sp.tw_r2r)[(int)(((long long)sp.r2r_a2 * (2 * k + sp.r2r_b2)) % (8ll * sp.r2r_D))];
+          const T re = v.x * w.x - v.y * w.y, im = v.x * w.y + v.y * w.x;
+          v.x = sp.r2r_sine ? (T)-2 * im : (T)2 * re;
+          v.y = 0;
+        }
         if (sp.mod_out.on && sign_mod(sp.mod_out, kk) < 0) { v.x = -v.x; v.y = -v.y; }
         if (sp.conj_out) v.y = -v.y;
         const int seg = kk / sp.oblk;

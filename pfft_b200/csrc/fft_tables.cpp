@@ -72,4 +72,23 @@ unsigned long long &launch_counter() {
   return n;
 }
 
+// DCT/DST kinds as FFTW defines them (fftw3.h r2r kinds 3..10; reference api/pfft.h:45-55):
+//   Y_k = 2 sum_j w_j X_j cos|sin(pi (j + a)(k + b) / D),  w = 1 except the halved end points
+//   of the types I and III.  Halfcomplex kinds (R2HC, HC2R, DHT) are out of scope.
+bool r2r_params(int kind, int n, int *a2, int *b2, int *D, int *sine, int *half0, int *halfn) {
+  *half0 = *halfn = 0;
+  switch (kind) {
+    case 3: *a2 = 0; *b2 = 0; *D = n - 1; *sine = 0; *half0 = 1; *halfn = 1; break;   // REDFT00 (DCT-I)
+    case 4: *a2 = 0; *b2 = 1; *D = n; *sine = 0; *half0 = 1; break;                    // REDFT01 (DCT-III)
+    case 5: *a2 = 1; *b2 = 0; *D = n; *sine = 0; break;                                // REDFT10 (DCT-II)
+    case 6: *a2 = 1; *b2 = 1; *D = n; *sine = 0; break;                                // REDFT11 (DCT-IV)
+    case 7: *a2 = 2; *b2 = 2; *D = n + 1; *sine = 1; break;                            // RODFT00 (DST-I)
+    case 8: *a2 = 2; *b2 = 1; *D = n; *sine = 1; *halfn = 1; break;                    // RODFT01 (DST-III)
+    case 9: *a2 = 1; *b2 = 2; *D = n; *sine = 1; break;                                // RODFT10 (DST-II)
+    case 10: *a2 = 1; *b2 = 1; *D = n; *sine = 1; break;                               // RODFT11 (DST-IV)
+    default: return false;
+  }
+  return *D >= 1;
+}
+
 }  // namespace pfb

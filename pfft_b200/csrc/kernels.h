@@ -36,6 +36,11 @@ struct StageParams {
   int in_real, out_real, conj_in, conj_out;
   SignModDev mod_in, mod_out;
   const void *twiddle;       // L entries exp(-2*pi*i*k/L) in the stage's precision
+  // r2r (DCT/DST): the line is transformed as a zero-padded complex DFT of length L = 2D with a
+  // twiddle before and after: Y_k = 2 F(sum_j w_j x_j exp(-i pi (j + a)(k + b) / D)), F = Re | -Im
+  const void *tw_r2r;        // 8D entries exp(-2*pi*i*m/(8D))
+  int r2r_a2, r2r_b2, r2r_D; // 2a, 2b, D
+  int r2r_sine, r2r_half0, r2r_halfn;   // F = -Im; w_0 = 1/2; w_{n-1} = 1/2
   int nfac;
   int fac[kMaxFactors];
   // power-of-two fast path (fft_pow2.cu)
@@ -60,7 +65,9 @@ struct FusePlanes {
 };
 
 // host-side helpers (fft_tables.cpp)
-int factorize_generic(int L, int *fac);          // radices for the generic shared-memory kernel
+int factorize_generic(int L, int *fac);
+// parameters of an r2r kind (FFTW's enum values) on a line of n reals; false: unsupported kind
+bool r2r_params(int kind, int n, int *a2, int *b2, int *D, int *sine, int *half0, int *halfn);          // radices for the generic shared-memory kernel
 void make_twiddles_f64(int L, double *re_im);    // 2*L doubles, accurate to < 1 ulp
 void make_twiddles_f32(int L, float *re_im);
 

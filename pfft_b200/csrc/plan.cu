@@ -99,15 +99,20 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     const Stage &g = s.stages[i];
     StageParams sp;
     memset(&sp, 0, sizeof sp);
-    if (g.op == OP_R2R) {
-      *err = "r2r transforms are not implemented yet";
-      return false;
-    }
-    if (g.n > (1 << 24)) {
+    if (g.n > (1 << 22)) {
       *err = "transform length too large";
       return false;
     }
-    const int L = (int)g.n;
+    int L = (int)g.n;
+    if (g.op == OP_R2R) {
+      // DCT/DST line of n reals = zero-padded complex DFT of length 2D between two twiddles (kernels.h)
+      if (!r2r_params(g.r2r_kind, (int)g.n, &sp.r2r_a2, &sp.r2r_b2, &sp.r2r_D, &sp.r2r_sine, &sp.r2r_half0, &sp.r2r_halfn)) {
+        *err = "r2r kind " + std::to_string(g.r2r_kind) + " on length " + std::to_string(g.n) +
+               " is not supported (DCT/DST kinds REDFT00..RODFT11 only)";
+        return false;
+      }
+      L = 2 * sp.r2r_D;
+    }
     sp.op = g.op;
     sp.sign = g.sign;
     sp.r2r_kind = g.r2r_kind;
@@ -172,6 +177,21 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
       }
       const TableSet &ts = it->second;
       sp.twiddle = ts.dev;
+      if (g.op == OP_R2R) {
+        const int M = 8 * sp.r2r_D;
+        auto jt = table_of.find(-M);
+        if (jt == table_of.end()) {
+          std::vector<double> roots(2 * (size_t)M);
+          make_twiddles_f64(M, roots.data());
+          std::vector<T> host(roots.begin(), roots.end());
+          void *dev = nullptr;
+          CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(T)));
+          CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+          pl->tables.push_back(dev);
+          jt = table_of.emplace(-M, TableSet{dev, 0, 0, false}).first;
+        }
+        sp.tw_r2r = jt->second.dev;
+      }
       if (fast) {
         sp.tw2 = static_cast<const T *>(ts.dev) + 2 * ts.off2;
         sp.tw3 = static_cast<const T *>(ts.dev) + 2 * ts.off3;

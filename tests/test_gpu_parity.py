@@ -74,6 +74,13 @@ SINGLE_RANK = [
     dict(kind="c2c", n=[8, 6, 4], np=[1, 1], flags=S_IN | S_OUT | T_OUT),
     dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[1, 1], flags=S_IN | S_OUT),
     dict(kind="c2c", n=[8, 6, 4], np=[1, 1], skip=[0, 1, 0]),
+    # r2r: DCT/DST kinds (FFTW enum values; reference tests/simple_check_r2r.c uses REDFT00/01/10, RODFT00)
+    dict(kind="r2r", n=[9, 8, 7], np=[1, 1], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
+    dict(kind="r2r", n=[9, 8, 7], np=[1, 1], kinds=[po.RODFT00, po.RODFT01, po.RODFT10], flags=T_OUT),
+    dict(kind="r2r", n=[6, 5, 12], np=[1, 1], kinds=[po.REDFT11, po.RODFT11, po.REDFT10], flags=T_IN),
+    dict(kind="r2r", n=[16, 16, 16], np=[1, 1], kinds=[po.REDFT10, po.REDFT10, po.REDFT10], precision="single"),
+    dict(kind="r2r", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[1, 1], kinds=[po.REDFT00, po.RODFT00, po.REDFT01]),
+    dict(kind="r2r", n=[64, 32, 128], np=[1, 1], kinds=[po.REDFT10, po.RODFT10, po.REDFT01], flags=T_OUT),
     # plane-fused last pair (power-of-two lines of equal length in the last two stages)
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_OUT, tag="-fused"),
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
@@ -115,6 +122,9 @@ MULTI_RANK = [
     dict(kind="c2r", n=[29, 27, 31], np=[2, 2], flags=T_IN, sign=+1),
     dict(kind="c2c", n=[32, 32, 32], np=[2, 2], flags=T_OUT, precision="single"),
     dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
+    dict(kind="r2r", n=[7, 6, 5, 4], np=[2, 2, 2], kinds=[po.REDFT10, po.RODFT00, po.REDFT00, po.RODFT01], flags=T_OUT),
 ]
 
 

@@ -20,7 +20,7 @@ def _list(name):
 
 
 # implemented today; everything else in LIST_2D/LIST_3D is expected to fail until its row lands
-NOT_YET = re.compile(r"r2r|(?<!ghost_c2c_)3d_on_3d")
+NOT_YET = re.compile(r"(?<!ghost_c2c_)3d_on_3d")
 PROGRAMS = [(n, 4) for n in _list("LIST_2D") if not n.startswith("time_")] + [(n, 8) for n in _list("LIST_3D")]
 
 

@@ -78,6 +78,12 @@ CASES = [
     dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_IN),
     dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_OUT),
     dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[2, 2], flags=S_IN | S_OUT),
+    # r2r (reference tests/simple_check_r2r*.c)
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT01, po.RODFT11, po.REDFT00], flags=T_IN),
+    dict(kind="r2r", n=[7, 6, 5, 4], np=[2, 2, 2], kinds=[po.REDFT10, po.RODFT00, po.REDFT00, po.RODFT01], flags=T_OUT),
+    dict(kind="r2r", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[2, 2], kinds=[po.REDFT00, po.RODFT00, po.REDFT01]),
 ]
 
 
