@@ -437,6 +437,8 @@ def mem_order(rnk_n, rnk_pm, transposed):
     transposed layout (doc/tutorial.tex:322-325; api/api-basic.c:1149-1183)."""
     if not transposed:
         return list(range(rnk_n))
+    if rnk_pm >= rnk_n:      # 3-D data on a 3-D mesh runs on a 2-D mesh internally (kernel/procmesh.c:191-205)
+        rnk_pm = rnk_n - 1
     return list(range(1, rnk_pm + 1)) + [0] + list(range(rnk_pm + 1, rnk_n))
 
 

@@ -16,6 +16,7 @@ constexpr int kMaxDims = 8;    // rnk_n
 constexpr int kMaxMesh = 3;    // rnk_pm
 constexpr int kMaxBatch = 4;   // batch dims a stage kernel indexes (after merging)
 constexpr int kMaxSeg = 32;    // ranks along one mesh dimension
+constexpr int kMaxGroups = 5;  // exchange groups of a schedule: mesh dimensions (+ 2 for the 3-D -> 2-D mesh remap)
 
 // public flag bits (include/pfft.h; reference api/pfft.h:528-545)
 enum : unsigned {
@@ -133,6 +134,14 @@ struct Schedule {
   int rnk_pm_eff = 0;           // mesh rank the schedule runs on (2 for a remapped 3-D mesh)
   int np_eff[kMaxMesh] = {1, 1, 1};
   int coords_eff[kMaxMesh] = {0, 0, 0};
+  // Exchange groups (Exchange::mesh_dim indexes them): the rows / columns of the mesh the
+  // schedule runs on and, for 3-D data on a 3-D mesh, the two sub-groups of the remap
+  // (reference kernel/procmesh.c:191-391).  members = ranks of the user's Cartesian communicator.
+  int ngroups = 0;
+  struct Group {
+    int size = 1, me = 0;
+    int members[kMaxSeg] = {0};
+  } groups[kMaxGroups];
   LocalSizes ls;
   std::vector<Stage> stages;
   std::vector<Exchange> exchanges;

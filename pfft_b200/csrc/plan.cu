@@ -378,11 +378,12 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
     return nullptr;
   }
   const Schedule &s = pl->sched;
-  const int r = s.rnk_pm_eff;
-  for (int t = 0; t < r; t++) {
-    int remain[kMaxMesh] = {0, 0, 0};
-    remain[t] = 1;
-    MPI_Cart_sub(pl->comm_cart, remain, &pl->comm_1d[t]);
+  // one communicator per exchange group (rows / columns of the mesh, remap sub-groups):
+  // colour = lowest member rank, key = position inside the group
+  for (int g = 0; g < s.ngroups; g++) {
+    int color = s.groups[g].members[0];
+    for (int q = 1; q < s.groups[g].size; q++) color = std::min(color, s.groups[g].members[q]);
+    MPI_Comm_split(pl->comm_cart, color, s.groups[g].me, &pl->comm_1d[g]);
   }
   const size_t rb = pl->elem_real_bytes();
   auto bytes_of = [&](const INT *ln, bool real) {
@@ -458,7 +459,7 @@ void plan_destroy(PlanBase *pl) {
   for (void *t : pl->tables) cudaFree(t);
   for (int k = 0; k < 3; k++)
     if (pl->scratch[k]) cudaFree(pl->scratch[k]);
-  for (int t = 0; t < kMaxMesh; t++)
+  for (int t = 0; t < kMaxGroups; t++)
     if (pl->comm_1d[t] != MPI_COMM_NULL) MPI_Comm_free(&pl->comm_1d[t]);
   if (pl->comm_cart != MPI_COMM_NULL) MPI_Comm_free(&pl->comm_cart);
   delete pl;

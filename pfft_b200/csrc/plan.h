@@ -51,7 +51,7 @@ struct PlanBase {
   Problem prob;
   Schedule sched;
   MPI_Comm comm_cart = MPI_COMM_NULL;
-  MPI_Comm comm_1d[kMaxMesh] = {MPI_COMM_NULL, MPI_COMM_NULL, MPI_COMM_NULL};
+  MPI_Comm comm_1d[kMaxGroups] = {MPI_COMM_NULL, MPI_COMM_NULL, MPI_COMM_NULL, MPI_COMM_NULL, MPI_COMM_NULL};   // one per exchange group
   void *planned_in = nullptr, *planned_out = nullptr;
   // device scratch: [0]=A, [1]=B (stage ping-pong / receive areas), [2]=W (NCCL send area)
   void *scratch[3] = {nullptr, nullptr, nullptr};

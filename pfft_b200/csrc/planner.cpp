@@ -65,7 +65,10 @@ struct Builder {
   const Problem &p;
   Schedule &s;
   int d, r;
-  int np[kMaxMesh], c[kMaxMesh];
+  int np[kMaxGroups], c[kMaxGroups];   // [0, r): mesh the pencil schedule runs on; then the remap groups
+  Mesh3dto2d m3;
+  int c3[3] = {0, 0, 0};
+  static constexpr int GQ1 = 2, GQ0 = 3;   // group ids of the remap sub-groups (size q1 / q0)
   unsigned tr;
   INT iblk[kMaxMesh], mblk[kMaxMesh], oblk[kMaxMesh];
   HalfSizes hs[2];
@@ -81,26 +84,64 @@ struct Builder {
     d = p.rnk_n;
     r = p.rnk_pm;
     tr = p.flags & (F_TRANSPOSED_IN | F_TRANSPOSED_OUT);
-    if (mesh_3dto2d(p).active) {
-      s.error = "3-D data on a 3-D process mesh (3dto2d remap) is not supported yet";
-      return false;
-    }
+    m3 = mesh_3dto2d(p);
     if (d > kMaxDims - 1 || r > kMaxMesh) {
       s.error = "too many dimensions";
       return false;
     }
-    mesh_coords(r, p.np, s.pid, c);
-    for (int t = 0; t < r; t++) {
-      np[t] = p.np[t];
+    for (int t = 0; t < kMaxGroups; t++) { np[t] = 1; c[t] = 0; }
+    if (m3.active) {
+      // 3-D data on a 3-D mesh P0 x P1 x (q0 q1): the transform runs as a pencil schedule on the
+      // 2-D mesh (P0 q0) x (P1 q1), reference kernel/procmesh.c:191-205, with a remap in front / behind
+      if (p.flags & F_PADDED_R2C) {
+        s.error = "PFFT_PADDED_R2C/C2R is not supported for 3-D data on a 3-D process mesh";
+        return false;
+      }
+      mesh_coords(3, p.np, s.pid, c3);
+      r = 2;
+      np[0] = p.np[0] * m3.q0;
+      np[1] = p.np[1] * m3.q1;
+      c[0] = c3[0] * m3.q0 + c3[2] / m3.q1;
+      c[1] = c3[1] * m3.q1 + c3[2] % m3.q1;
+      np[GQ1] = m3.q1;
+      c[GQ1] = c3[2] % m3.q1;
+      np[GQ0] = m3.q0;
+      c[GQ0] = c3[2] / m3.q1;
+    } else {
+      mesh_coords(r, p.np, s.pid, c);
+      for (int t = 0; t < r; t++) np[t] = p.np[t];
+    }
+    for (int t = 0; t < kMaxGroups; t++)
       if (np[t] > kMaxSeg) {
         s.error = "mesh dimension larger than 32";
         return false;
       }
-    }
     s.rnk_pm_eff = r;
     for (int t = 0; t < r; t++) {
       s.np_eff[t] = np[t];
       s.coords_eff[t] = c[t];
+    }
+    // exchange groups as ranks of the user's Cartesian communicator (row-major, last fastest)
+    if (m3.active) {
+      const int P1 = p.np[1], P2 = p.np[2], q0 = m3.q0, q1 = m3.q1;
+      auto rank3 = [&](int a, int b, int cc) { return (a * P1 + b) * P2 + cc; };
+      s.ngroups = 4;
+      for (int g = 0; g < 4; g++) { s.groups[g].size = np[g]; s.groups[g].me = c[g]; }
+      for (int e = 0; e < np[0]; e++) s.groups[0].members[e] = rank3(e / q0, c3[1], (e % q0) * q1 + c3[2] % q1);
+      for (int e = 0; e < np[1]; e++) s.groups[1].members[e] = rank3(c3[0], e / q1, (c3[2] / q1) * q1 + e % q1);
+      for (int j = 0; j < q1; j++) s.groups[GQ1].members[j] = rank3(c3[0], c3[1], (c3[2] / q1) * q1 + j);
+      for (int i = 0; i < q0; i++) s.groups[GQ0].members[i] = rank3(c3[0], c3[1], i * q1 + c3[2] % q1);
+    } else {
+      s.ngroups = r;
+      for (int m = 0; m < r; m++) {
+        s.groups[m].size = np[m];
+        s.groups[m].me = c[m];
+        for (int q = 0; q < np[m]; q++) {
+          int rk = 0;
+          for (int t = 0; t < r; t++) rk = rk * np[t] + (t == m ? q : c[t]);
+          s.groups[m].members[q] = rk;
+        }
+      }
     }
     // blocks, reference kernel/partrafo.c:652-701
     INT pni[kMaxDims], pno[kMaxDims];
@@ -112,10 +153,12 @@ struct Builder {
     const INT *mu = nullptr;
     if (tr & F_TRANSPOSED_IN) mu = p.has_iblock ? p.iblock : nullptr;
     if (tr & F_TRANSPOSED_OUT) mu = p.has_oblock ? p.oblock : nullptr;
+    const bool ub = !m3.active;   // user block sizes do not apply to the remapped mesh (kernel/remap_3dto2d.c:36)
+    if (!ub) mu = nullptr;
     for (int t = 0; t < r; t++) {
-      iblk[t] = block_default(pni[t], p.has_iblock && !(tr & F_TRANSPOSED_IN) ? p.iblock[t] : 0, np[t]);
+      iblk[t] = block_default(pni[t], ub && p.has_iblock && !(tr & F_TRANSPOSED_IN) ? p.iblock[t] : 0, np[t]);
       mblk[t] = block_default(pnm[t + 1], mu ? mu[t] : 0, np[t]);
-      oblk[t] = block_default(pno[t], p.has_oblock && !(tr & F_TRANSPOSED_OUT) ? p.oblock[t] : 0, np[t]);
+      oblk[t] = block_default(pno[t], ub && p.has_oblock && !(tr & F_TRANSPOSED_OUT) ? p.oblock[t] : 0, np[t]);
     }
     // the two halves, reference kernel/partrafo.c:735-834
     HalfSizes &to = hs[0], &ti = hs[1];
@@ -419,6 +462,47 @@ struct Builder {
         if (ti.trafo) for (int a = r + 1; a < d; a++) steps.push_back({a, true, 1});
       }
     }
+    if (m3.active && !local_only) {
+      // 3-D blocks <-> pencils of the 2-D mesh, reference kernel/remap_3dto2d.c:219-338: two
+      // exchanges inside the sub-groups of size q1 and q0 (block sizes kernel/remap_3dto2d.c:437-457).
+      // A stage splits and gathers along the dimension it walks, hence a dense re-layout stage
+      // between the two exchanges.
+      const int q0 = m3.q0, q1 = m3.q1;
+      if (to.active) {
+        // sizes of the arriving array: logical reals for r2c input, else as stored
+        INT nn[3];
+        for (int t = 0; t < 3; t++) nn[t] = (to.kind == Kind::R2C) ? to.ni[t] : phys(to.kind, to.ni, t);
+        const INT ob0 = block_default(nn[0], 0, np[0]), ob1 = block_default(nn[1], 0, np[1]);
+        const INT ib2 = block_default(nn[2], 0, q0 * q1), mb2 = ib2 * q1;
+        const INT l0 = block_extent(nn[0], ob0 * q0, c3[0]), l1 = block_extent(nn[1], ob1 * q1, c3[1]);
+        Step a{1, false, 0}, b{2, false, 0}, cst{0, false, 0};
+        a.xch_mesh = GQ1; a.xch_split = 1; a.xch_gather = 2;
+        a.split_blk = ob1; a.split_n = l1; a.gather_blk = ib2; a.gather_n = block_extent(nn[2], mb2, c[GQ0]);
+        cst.xch_mesh = GQ0; cst.xch_split = 0; cst.xch_gather = 2;
+        cst.split_blk = ob0; cst.split_n = l0; cst.gather_blk = mb2; cst.gather_n = nn[2];
+        steps.insert(steps.begin(), {a, b, cst});
+      }
+      if (ti.active) {
+        INT nn[3];
+        for (int t = 0; t < 3; t++) nn[t] = (ti.kind == Kind::C2R) ? ti.no[t] : phys(ti.kind, ti.no, t);
+        const INT ob0 = block_default(nn[0], 0, np[0]), ob1 = block_default(nn[1], 0, np[1]);
+        const INT ib2 = block_default(nn[2], 0, q0 * q1), mb2 = ib2 * q1;
+        const INT l0 = block_extent(nn[0], ob0 * q0, c3[0]), l1 = block_extent(nn[1], ob1 * q1, c3[1]);
+        Step &lastti = steps.back();   // walks dimension 2 and has no exchange yet
+        if (lastti.dim != 2 || lastti.xch_mesh >= 0) {
+          s.error = "internal: unexpected last stage in front of the 2d->3d remap";
+          return false;
+        }
+        lastti.xch_mesh = GQ0; lastti.xch_split = 2; lastti.xch_gather = 0;
+        lastti.split_blk = mb2; lastti.split_n = nn[2]; lastti.gather_blk = ob0; lastti.gather_n = l0;
+        Step b{0, false, 1}, cst{2, false, 1}, e{1, false, 1};
+        cst.xch_mesh = GQ1; cst.xch_split = 2; cst.xch_gather = 1;
+        cst.split_blk = ib2; cst.split_n = block_extent(nn[2], mb2, c[GQ0]); cst.gather_blk = ob1; cst.gather_n = l1;
+        steps.push_back(b);
+        steps.push_back(cst);
+        steps.push_back(e);
+      }
+    }
     if (steps.empty()) {
       s.error = "empty schedule";
       return false;
@@ -604,6 +688,12 @@ std::string schedule_to_json(const Schedule &s) {
   for (int t = 0; t < s.rnk_pm_eff; t++) o << (t ? "," : "") << s.coords_eff[t];
   o << "],\"np\":[";
   for (int t = 0; t < s.rnk_pm_eff; t++) o << (t ? "," : "") << s.np_eff[t];
+  o << "],\"groups\":[";
+  for (int g = 0; g < s.ngroups; g++) {
+    o << (g ? "," : "") << "{\"size\":" << s.groups[g].size << ",\"me\":" << s.groups[g].me << ",\"members\":[";
+    for (int q = 0; q < s.groups[g].size; q++) o << (q ? "," : "") << s.groups[g].members[q];
+    o << "]}";
+  }
   o << "],\"stages\":[";
   for (size_t i = 0; i < s.stages.size(); i++) {
     const Stage &g = s.stages[i];

@@ -29,7 +29,7 @@ struct PeerMap {
   std::vector<void *> ptr[2];
   std::vector<void *> opened;   // to close
   // cart rank of member q of mesh dimension m
-  std::vector<int> member_rank[kMaxMesh];
+  std::vector<int> member_rank[kMaxGroups];
 };
 
 namespace {
@@ -78,17 +78,7 @@ std::map<std::vector<int>, ncclComm_t> &nccl_cache() {
 void fill_members(PlanBase *pl) {
   PeerMap *pm = pl->peers;
   const Schedule &s = pl->sched;
-  for (int m = 0; m < s.rnk_pm_eff; m++) {
-    pm->member_rank[m].resize(s.np_eff[m]);
-    for (int q = 0; q < s.np_eff[m]; q++) {
-      int coords[kMaxMesh];
-      for (int t = 0; t < s.rnk_pm_eff; t++) coords[t] = s.coords_eff[t];
-      coords[m] = q;
-      int rk = 0;
-      MPI_Cart_rank(pl->comm_cart, coords, &rk);
-      pm->member_rank[m][q] = rk;
-    }
-  }
+  for (int g = 0; g < s.ngroups; g++) pm->member_rank[g].assign(s.groups[g].members, s.groups[g].members + s.groups[g].size);
 }
 
 }  // namespace

@@ -154,10 +154,10 @@ def simulate(scheds, user_in):
         for r in range(P):
             s = scheds[r]
             x = s["exchanges"][xi]
+            grp = s["groups"][x["mesh_dim"]]
+            assert grp["size"] == x["nparts"] and grp["me"] == x["me"] and grp["members"][x["me"]] == r
             for q in range(x["nparts"]):
-                coords = list(s["coords"])
-                coords[x["mesh_dim"]] = q
-                dst = rank_of(s["np"], coords)
+                dst = grp["members"][q]
                 xd = scheds[dst]["exchanges"][xi]
                 chunk = outs[r][q]
                 assert chunk.size == x["send_cnt"][q]

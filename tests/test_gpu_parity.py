@@ -122,6 +122,12 @@ MULTI_RANK = [
     dict(kind="c2r", n=[29, 27, 31], np=[2, 2], flags=T_IN, sign=+1),
     dict(kind="c2c", n=[32, 32, 32], np=[2, 2], flags=T_OUT, precision="single"),
     dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[2, 2], flags=T_OUT),
+    # 3-D data on a 3-D mesh (3dto2d remap)
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2]),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_IN, sign=+1),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[64, 64, 64], np=[1, 2, 4], flags=T_OUT),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
     dict(kind="r2r", n=[7, 6, 5, 4], np=[2, 2, 2], kinds=[po.REDFT10, po.RODFT00, po.REDFT00, po.RODFT01], flags=T_OUT),

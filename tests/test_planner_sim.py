@@ -78,6 +78,20 @@ CASES = [
     dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_IN),
     dict(kind="c2c", n=[8, 6, 4], np=[2, 2], flags=S_OUT),
     dict(kind="c2c", n=[16, 12, 8], ni=[8, 6, 4], no=[16, 12, 8], np=[2, 2], flags=S_IN | S_OUT),
+    # 3-D data on a 3-D mesh (3dto2d remap, reference tests/simple_check_*_3d_on_3d*.c)
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2]),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[9, 8, 7], np=[1, 1, 4]),
+    dict(kind="c2c", n=[9, 8, 7], np=[2, 1, 3], flags=T_OUT),
+    dict(kind="c2c", n=[5, 4, 3], np=[1, 2, 6]),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2, 2]),
+    dict(kind="r2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
+    dict(kind="c2r", n=[29, 27, 31], np=[2, 2, 2], sign=+1),
+    dict(kind="c2r", n=[29, 27, 31], np=[2, 2, 2], flags=T_IN, sign=+1),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
+    dict(kind="r2r", n=[13, 11, 9], np=[2, 2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
+    dict(kind="c2c", n=[8, 8, 8], np=[1, 1, 1]),
     # r2r (reference tests/simple_check_r2r*.c)
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
