@@ -152,6 +152,14 @@ __device__ __forceinline__ int phys(int idx) { return idx + (idx >> 4); }
 template <int N>
 constexpr int line_pitch(int skew) { return N + (N >> 4) + skew; }
 
+// phys(i + e * STEP) given i (and pi = phys(i)): for steps that are multiples of 16 the padding
+// advances by STEP / 16 per step, so the address is pi + a compile-time constant
+template <int STEP>
+__device__ __forceinline__ int phys_at(int i, int pi, int e) {
+  if (STEP % 16 == 0) return pi + e * (STEP + STEP / 16);
+  return phys(i + e * STEP);
+}
+
 // One Stockham pass on the E register-resident points of a line.
 //  R : radix, NS : product of the radices of earlier passes, LAST : outputs stay in registers.
 //  twp : this pass' twiddles laid out [r-1][k] (k < NS), so that neighbouring threads read
@@ -186,8 +194,18 @@ __device__ __forceinline__ void pass(cx<T> *x, int t, const cx<T> *__restrict__ 
       for (int q = 0; q < R; q++) x[b + q * B] = v[slot_of<R>(q)];
     } else {
       const int base = ((j - k) * R) + k;   // (j / NS) * NS * R + k
+      if (NS % 16 == 0) {
+        const int pb = phys(base);
 #pragma unroll
-      for (int q = 0; q < R; q++) line_smem[phys(base + q * NS)] = v[slot_of<R>(q)];
+        for (int q = 0; q < R; q++) line_smem[pb + q * (NS + NS / 16)] = v[slot_of<R>(q)];
+      } else if (NS == 1 && R == 16) {
+        const int pb = 17 * j;                // phys(16 j + q) = 16 j + q + j for q < 16
+#pragma unroll
+        for (int q = 0; q < R; q++) line_smem[pb + q] = v[slot_of<R>(q)];
+      } else {
+#pragma unroll
+        for (int q = 0; q < R; q++) line_smem[phys(base + q * NS)] = v[slot_of<R>(q)];
+      }
     }
   }
 }
@@ -522,6 +540,7 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
   const bool per_line = (THREADS % 32 == 0) && tl <= 15;
   cx<T> *const my_line_in = smem + tt_in * pitch;
   const unsigned my_line_in_s = (unsigned)__cvta_generic_to_shared(my_line_in);
+  const int pt_in = phys(t_in);
   auto sync_lines = [&](bool pl) {
     if (pl) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_in), "n"(THREADS) : "memory");
     else __syncthreads();
@@ -616,7 +635,7 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
     if (tt_in < tvalid) {
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const unsigned dst = my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>));
+        const unsigned dst = my_line_in_s + (unsigned)(phys_at<THREADS>(t_in, pt_in, e) * sizeof(cx<T>));
         if (FUSED) cp_async_zfill_hint<sizeof(cx<T>)>(dst, in + sp.in_off[e], true, pol);
         else cp_async_plain<sizeof(cx<T>)>(dst, in + sp.in_off[e]);
       }
@@ -662,7 +681,7 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
     asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
     for (int e = 0; e < E; e++) {
-      const cx<T> r = my_line_in[phys(t_in + e * THREADS)];
+      const cx<T> r = my_line_in[phys_at<THREADS>(t_in, pt_in, e)];
       x[e].x = backward ? r.y : r.x;
       x[e].y = backward ? r.x : r.y;
     }
@@ -671,15 +690,16 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
     if (P::NPASS == 3) {
       sync_lines(per_line);
 #pragma unroll
-      for (int e = 0; e < E; e++) x[e] = my_line_in[phys(t_in + e * THREADS)];
+      for (int e = 0; e < E; e++) x[e] = my_line_in[phys_at<THREADS>(t_in, pt_in, e)];
       sync_lines(per_line);
       pass<T, N, E, P::R2, P::R1, false>(x, t_in, tw2, my_line_in);
     }
     sync_lines(lbar_out);
     {
       const cx<T> *line_r = smem + tt_out * pitch;
+      const int pt_out = phys(t_out);
 #pragma unroll
-      for (int e = 0; e < E; e++) x[e] = line_r[phys(t_out + e * THREADS)];
+      for (int e = 0; e < E; e++) x[e] = line_r[phys_at<THREADS>(t_out, pt_out, e)];
     }
     unsigned next;
     if (FUSED) {
