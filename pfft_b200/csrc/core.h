@@ -16,6 +16,7 @@ constexpr int kMaxDims = 8;    // rnk_n
 constexpr int kMaxMesh = 3;    // rnk_pm
 constexpr int kMaxBatch = 4;   // batch dims a stage kernel indexes (after merging)
 constexpr int kMaxSeg = 32;    // ranks along one mesh dimension
+constexpr int kMaxTile = 64;   // lines of an explicit tile (micro-blocked layouts)
 constexpr int kMaxGroups = 5;  // exchange groups of a schedule: mesh dimensions (+ 2 for the 3-D -> 2-D mesh remap)
 
 // public flag bits (include/pfft.h; reference api/pfft.h:528-545)
@@ -104,6 +105,15 @@ struct Stage {
   int nbatch = 0;
   BatchDim batch[kMaxBatch];
   int tile_dim = -1;          // index into batch[]: lines of one tile differ along it
+  // Micro-blocked layouts (planner.cpp: plan_microblocks).  Along `dim`, inside a chunk, index x sits at
+  //   (x / iblk2) * iblk2_stride + (x % iblk2) * istride      (same with o... on the output side);
+  // 1 = plain.  With ntile > 0 the tile is explicit: its lines are the combinations of the low parts
+  // of the micro-blocked batch dimensions, line l at tile_ioff[l] / tile_ooff[l] from the tile's base,
+  // and batch[] enumerates whole tiles (tile_dim = -1).
+  INT iblk2 = 1, iblk2_stride = 0;
+  INT oblk2 = 1, oblk2_stride = 0;
+  int ntile = 0;
+  INT tile_ioff[kMaxTile] = {0}, tile_ooff[kMaxTile] = {0};
   bool in_real = false, out_real = false;
   bool conj_in = false, conj_out = false;
   SignMod mod_in, mod_out;
@@ -152,6 +162,10 @@ struct Schedule {
 // Build the schedule of rank `pid`. Returns false (with sched->error) when the
 // configuration is legal for the reference but not yet supported here.
 bool build_schedule(const Problem &p, int pid, Schedule *sched);
+// Thread geometry of the register-resident power-of-two kernels, shared by the planner (tile shapes
+// of micro-blocked layouts) and fft_pow2.cu: points per thread, threads per line, lines per 512-thread tile.
+int pow2_points_per_thread(int L);
+inline int pow2_threads_per_line(int L) { return L / pow2_points_per_thread(L); }
 std::string schedule_to_json(const Schedule &s);
 
 }  // namespace pfb

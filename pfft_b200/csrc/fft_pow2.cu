@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -815,6 +816,334 @@ cudaError_t launch_fused_variant(StageParams &a, StageParams &b, FusePlanes &fp,
   return launch_fused_class<T, N, E, (THREADS > 512 ? THREADS : 512)>(a, b, fp, stream);
 }
 
+
+// ---- micro-blocked stages ------------------------------------------------------------------
+// Stage of a chain of power-of-two transforms whose intermediate arrays are stored as dense
+// micro-blocks (planner.cpp: plan_microblocks).  A tile is `tl` whole lines given by an offset
+// table; on a blocked side the lines of a tile interleave inside the blocks, so
+//   * loads from a blocked input use the tile-minor thread mapping (lane -> line first, then
+//     point): a warp fetches whole blocks, 512 / 256 contiguous bytes at 1024^3 fp64;
+//   * the butterflies always run line-major (a line belongs to whole warps: per-line named
+//     barriers between the passes);
+//   * stores to a blocked output use the tile-minor mapping again -- the change of mapping
+//     happens inside the last exchange through shared memory, as in the plain kernels.
+// User-facing sides (first stage's input, last stage's output) are contiguous lines and keep the
+// line-major mapping.  Every address is  tile base + thread base + table[e].
+//
+// One 512-thread CTA per SM owns the whole register file (16 points x 2 x fp64 per thread), so
+// nothing but this CTA can cover its memory latency.  Hence the tile is DOUBLE-BUFFERED: the
+// inputs of tile i+1 stream (cp.async, completion counted by an mbarrier) into a staging buffer
+// of their own during ALL of tile i's passes, and the exchanges between the passes go through a
+// second buffer.  Both fit because the exchange buffer holds 8-byte words only: fp64 lines are
+// exchanged in two rounds (real parts, then imaginary parts), fp32 lines as whole complex words.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+// arrival that fires when all cp.async of this thread issued so far have landed (counted in the init count)
+__device__ __forceinline__ void mbar_arrive_cp_async(unsigned bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+
+// butterflies of one pass, outputs left in registers: output q of butterfly b in x[b + q * B].
+// W3MUL (radix 4 only): the table holds w^k and w^2k; w^3k is their product.
+template <typename T, int N, int E, int R, int NS, bool W3MUL>
+__device__ __forceinline__ void pass_regs(cx<T> *x, int t, const cx<T> *__restrict__ twp) {
+  if constexpr (!W3MUL) {
+    pass<T, N, E, R, NS, true>(x, t, twp, nullptr);
+  } else {
+    static_assert(R == 4, "w^3 = w * w^2 is for the radix-4 pass");
+    constexpr int THREADS = N / E;
+    constexpr int B = E / R;
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+      const int k = (t + b * THREADS) & (NS - 1);
+      const cx<T> w1 = twp[k], w2 = twp[NS + k];
+      cx<T> v[4] = {x[b], cmul(x[b + B], w1), cmul(x[b + 2 * B], w2), cmul(x[b + 3 * B], cmul(w1, w2))};
+      dft4(v[0], v[1], v[2], v[3]);
+      x[b] = v[0]; x[b + B] = v[1]; x[b + 2 * B] = v[2]; x[b + 3 * B] = v[3];
+    }
+  }
+}
+// where pass (R, NS) puts output q of butterfly b: index into a padded line of 8-byte words
+template <int N, int E, int R, int NS>
+__device__ __forceinline__ int scatter_index(int t, int b, int q) {
+  constexpr int THREADS = N / E;
+  const int j = t + b * THREADS;
+  const int k = j & (NS - 1);
+  const int base = ((j - k) * R) + k;
+  if (NS % 16 == 0) return phys(base) + q * (NS + NS / 16);
+  if (NS == 1 && R == 16) return 17 * j + q;
+  return phys(base + q * NS);
+}
+// PART 0: real parts, 1: imaginary parts (XE = T); 2: whole complex words (XE = cx<T>)
+template <typename T, int N, int E, int R, int NS, int PART, typename XE>
+__device__ __forceinline__ void scatter(const cx<T> *x, int t, XE *line) {
+  constexpr int B = E / R;
+#pragma unroll
+  for (int b = 0; b < B; b++)
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const int idx = scatter_index<N, E, R, NS>(t, b, q);
+      if constexpr (PART == 0) line[idx] = x[b + q * B].x;
+      else if constexpr (PART == 1) line[idx] = x[b + q * B].y;
+      else line[idx] = x[b + q * B];
+    }
+}
+
+// TMA bulk copy global -> shared of `bytes` (multiple of 16, both addresses 16-byte aligned); completion is
+// counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// Geometry of the staging buffer, shared by the kernel and its launcher.
+//  line-major input: lines are dense (pitch N), fetched in pieces of <= 2 KB;
+//  blocked input: one piece per micro-block, kept dense, blocks padded by one line-piece so that the
+//  strided reads of a line (tG words out of every block) fall into different banks.
+struct StageGeom {
+  int blocked, nchunks, chunk_elems, pitch;   // pitch: of a line (line-major) / of a block (blocked), in complex words
+  long long words;                            // complex words of the staging buffer
+};
+__host__ __device__ inline StageGeom stage_geom(int N, int tl, int iblk2, int elem_bytes) {
+  StageGeom g;
+  g.blocked = iblk2 > 1;
+  if (g.blocked) {
+    g.chunk_elems = tl * iblk2;
+    g.nchunks = N / iblk2;
+    g.pitch = g.chunk_elems + iblk2;
+    g.words = (long long)g.nchunks * g.pitch;
+  } else {
+    int cpl = N * elem_bytes / 2048;
+    if (cpl < 1) cpl = 1;
+    g.chunk_elems = N / cpl;
+    g.nchunks = tl * cpl;
+    g.pitch = N;
+    g.words = (long long)tl * N;
+  }
+  return g;
+}
+
+template <typename T, int N, int E, int MAXT, bool BWD>
+__global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constant__ StageParams sp) {
+  using P = Passes<N, E>;
+  using V = typename C2<T>::type;
+  constexpr int THREADS = N / E;
+  constexpr bool SPLIT = sizeof(T) == 8;                 // exchange real and imaginary parts separately
+  using XE = typename std::conditional<SPLIT, T, cx<T>>::type;   // 8-byte exchange word
+  static_assert(sizeof(XE) == 8, "exchange words are 8 bytes");
+  // the last radix-4 pass of N = 1024 keeps w^k and w^2k in shared memory and multiplies them for w^3k
+  constexpr bool W3MUL = P::NPASS == 3 && P::R3 == 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tl = sp.tl;
+  const StageGeom sg = stage_geom(N, tl, sp.iblk2, (int)sizeof(cx<T>));
+  // exchange buffer: lines of a tile must fall into different banks for the tile-minor gathers
+  // (8 lines x 2 x 8-byte words per half-warp: pitch = 2 mod 16)
+  const int pitch_x = N + (N >> 4) + 2;
+  cx<T> *stage = reinterpret_cast<cx<T> *>(smem_raw);
+  XE *xbuf = reinterpret_cast<XE *>(stage + sg.words);
+  constexpr int TW2 = (P::R2 - 1) * P::R1;
+  constexpr int TW3 = P::NPASS == 3 ? ((W3MUL ? 2 : P::R3 - 1)) * P::R1 * P::R2 : 0;
+  cx<T> *tw_s = reinterpret_cast<cx<T> *>(xbuf + (size_t)tl * pitch_x);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(tw_s + TW2 + TW3);
+  const int tid = threadIdx.x;
+  {
+    const cx<T> *g2 = reinterpret_cast<const cx<T> *>(sp.tw2);
+    for (int i = tid; i < TW2 + TW3; i += blockDim.x) tw_s[i] = g2[i];   // (tables are contiguous, [r-1][k])
+  }
+  const unsigned bar_full = (unsigned)__cvta_generic_to_shared(bars);
+  const unsigned bar_empty = bar_full + 8;
+  if (tid == 0) {
+    mbar_init(bar_full, 1);
+    mbar_init(bar_empty, blockDim.x);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const cx<T> *tw2 = tw_s;
+  const cx<T> *tw3 = tw_s + TW2;
+  __syncthreads();
+
+  const bool out_lm = sp.oblk2 == 1;                             // line-major mapping on the output side
+  const int t_c = tid % THREADS, tt_c = tid / THREADS;           // butterflies
+  const int t_s = out_lm ? t_c : tid / tl, tt_s = out_lm ? tt_c : tid % tl;
+  const bool per_line = (THREADS % 32 == 0) && tl <= 15;
+  const bool lbar_out = per_line && out_lm;
+  auto sync_lines = [&](bool pl) {
+    if (pl) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_c), "n"(THREADS) : "memory");
+    else __syncthreads();
+  };
+  // my E input points inside the staging buffer: first + e * step
+  const cx<T> *my_first;
+  int my_step;
+  if (sg.blocked) {
+    my_first = stage + (t_c / sp.iblk2) * sg.pitch + (int)sp.tile_ioff[tt_c] + (t_c % sp.iblk2);
+    my_step = (THREADS / sp.iblk2) * sg.pitch;
+  } else {
+    my_first = stage + tt_c * N + t_c;
+    my_step = THREADS;
+  }
+  XE *const my_x = xbuf + tt_c * pitch_x;
+  const XE *const out_x = xbuf + tt_s * pitch_x;
+  const int pt_c = phys(t_c), pt_s = phys(t_s);
+  // the piece of the tile this thread fetches (TMA bulk copy), if any
+  const bool loader = tid < sg.nchunks;
+  const unsigned chunk_bytes = (unsigned)(sg.chunk_elems * sizeof(cx<T>));
+  const unsigned tile_bytes = chunk_bytes * (unsigned)sg.nchunks;
+  const cx<T> *chunk_src = reinterpret_cast<const cx<T> *>(sp.in);
+  unsigned chunk_dst = (unsigned)__cvta_generic_to_shared(stage);
+  if (loader) {
+    if (sg.blocked) {
+      const long long j0 = (long long)tid * sp.iblk2;             // first line index of block `tid`
+      const long long seg = sp.iseg_stride ? j0 / sp.iblk : 0;
+      chunk_src += seg * sp.iseg_stride + ((j0 - seg * sp.iblk) / sp.iblk2) * sp.iblk2_stride;
+      chunk_dst += (unsigned)(tid * sg.pitch * sizeof(cx<T>));
+    } else {
+      const int cpl = sg.nchunks / tl, l = tid / cpl, part = tid % cpl;
+      chunk_src += sp.tile_ioff[l] + (long long)part * sg.chunk_elems;
+      chunk_dst += (unsigned)((l * N + part * sg.chunk_elems) * sizeof(cx<T>));
+    }
+  }
+  const long long out_thread = sp.tile_ooff[tt_s] +
+                               (out_lm ? (long long)t_s * sp.ostride
+                                       : (long long)(t_s / sp.oblk2) * sp.oblk2_stride + (long long)(t_s % sp.oblk2) * sp.ostride);
+  const unsigned ntiles = (unsigned)sp.ntiles;
+  auto locate = [&](unsigned tile, long long &ibase, long long &obase) {
+    unsigned rest = tile;
+    ibase = 0;
+    obase = 0;
+#pragma unroll
+    for (int k = kMaxBatch - 1; k >= 0; k--) {
+      if (k >= sp.nbatch) continue;
+      const unsigned ext = (unsigned)sp.bext[k];
+      const unsigned c = rest % ext;
+      rest /= ext;
+      ibase += (long long)c * sp.bis[k];
+      obase += (long long)c * sp.bos[k];
+    }
+  };
+  auto prefetch = [&](long long ibase) {
+    if (tid == 0) mbar_arrive_expect_tx(bar_full, tile_bytes);
+    if (loader) bulk_load(chunk_dst, chunk_src + ibase, chunk_bytes, bar_full);
+  };
+
+  long long ibase = 0, obase = 0;
+  unsigned tile = blockIdx.x;
+  if (tile < ntiles) {
+    locate(tile, ibase, obase);
+    prefetch(ibase);
+  }
+  unsigned phase = 0;
+  for (; tile < ntiles; tile += gridDim.x, phase ^= 1) {
+    cx<T> x[E];
+    mbar_wait(bar_full, phase);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      const cx<T> r = my_first[e * my_step];
+      x[e].x = BWD ? r.y : r.x;
+      x[e].y = BWD ? r.x : r.y;
+    }
+    mbar_arrive(bar_empty);          // my part of the staging buffer may be overwritten
+    pass_regs<T, N, E, P::R1, 1, false>(x, t_c, nullptr);
+    const long long obase_cur = obase;
+    const unsigned next = tile + gridDim.x;
+    if (next < ntiles) locate(next, ibase, obase);
+    // tile-minor output: the previous tile's last gather read every line of xbuf; everybody is past it once
+    // everybody has emptied the staging buffer of this tile
+    if (!lbar_out) mbar_wait(bar_empty, phase);
+#define PFB_EXCHANGE(R_, NS_, SRC, T_, PT_, PL)                                             \
+  if constexpr (SPLIT) {                                                                    \
+    T re_[E];                                                                               \
+    scatter<T, N, E, R_, NS_, 0>(x, t_c, my_x);                                             \
+    sync_lines(PL);                                                                         \
+    _Pragma("unroll") for (int e = 0; e < E; e++) re_[e] = (SRC)[phys_at<THREADS>(T_, PT_, e)];   \
+    sync_lines(PL);                                                                         \
+    scatter<T, N, E, R_, NS_, 1>(x, t_c, my_x);                                             \
+    sync_lines(PL);                                                                         \
+    _Pragma("unroll") for (int e = 0; e < E; e++) {                                         \
+      x[e].y = (SRC)[phys_at<THREADS>(T_, PT_, e)];                                         \
+      x[e].x = re_[e];                                                                      \
+    }                                                                                       \
+  } else {                                                                                  \
+    scatter<T, N, E, R_, NS_, 2>(x, t_c, my_x);                                             \
+    sync_lines(PL);                                                                         \
+    _Pragma("unroll") for (int e = 0; e < E; e++) x[e] = (SRC)[phys_at<THREADS>(T_, PT_, e)];     \
+  }
+    if (P::NPASS == 3) {
+      PFB_EXCHANGE(P::R1, 1, my_x, t_c, pt_c, per_line)
+      sync_lines(per_line);          // the line's words are free again
+      pass_regs<T, N, E, P::R2, P::R1, false>(x, t_c, tw2);
+    }
+    // fetch the next tile (its staging buffer must have been emptied by everybody; that was long ago)
+    if (next < ntiles) {
+      if (lbar_out && (loader || tid == 0)) mbar_wait(bar_empty, phase);
+      prefetch(ibase);
+    }
+    if (P::NPASS == 3) {
+      PFB_EXCHANGE(P::R2, P::R1, out_x, t_s, pt_s, lbar_out)
+      if (lbar_out) sync_lines(true);
+      pass_regs<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, W3MUL>(x, t_s, tw3);
+    } else {
+      PFB_EXCHANGE(P::R1, 1, out_x, t_s, pt_s, lbar_out)
+      if (lbar_out) sync_lines(true);
+      pass_regs<T, N, E, P::R2, P::R1, false>(x, t_s, tw2);
+    }
+#undef PFB_EXCHANGE
+    const long long thread_off = obase_cur + out_thread;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+      V raw;
+      raw.x = BWD ? x[e].y : x[e].x;
+      raw.y = BWD ? x[e].x : x[e].y;
+      cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[sp.out_seg[e]]) + thread_off + sp.out_off[e];
+      *reinterpret_cast<V *>(out) = raw;
+    }
+  }
+}
+
+template <typename T, int N, int E, int MAXT>
+cudaError_t launch_blk_class(StageParams &sp, cudaStream_t stream) {
+  constexpr int THREADS = N / E;
+  using P = Passes<N, E>;
+  constexpr bool W3MUL = P::NPASS == 3 && P::R3 == 4;
+  constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (W3MUL ? 2 : P::R3 - 1) * P::R1 * P::R2 : 0);
+  const int tl = sp.tl;
+  const StageGeom sg = stage_geom(N, tl, sp.iblk2, 2 * (int)sizeof(T));
+  const size_t pitch_x = N + (N >> 4) + 2;
+  const size_t smem = (size_t)sg.words * 2 * sizeof(T) + tl * pitch_x * 8 + (size_t)TWN * 2 * sizeof(T) + 16;
+  auto kf = stage_blk_kernel<T, N, E, MAXT, false>;
+  auto kb = stage_blk_kernel<T, N, E, MAXT, true>;
+  auto kern = sp.sign > 0 ? kb : kf;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (smem > 227 * 1024 || tl * THREADS > MAXT || sg.nchunks > tl * THREADS) return cudaErrorInvalidValue;
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl * THREADS, smem);
+  if (per_sm < 1) return cudaErrorInvalidValue;
+  const long long grid = std::min<long long>(sp.ntiles, (long long)sms * per_sm);
+  kern<<<(unsigned)grid, tl * THREADS, smem, stream>>>(sp);
+  launch_counter()++;
+  return cudaGetLastError();
+}
+
 // (N, E) pairs compiled in; E = points per thread.  Two block-size classes per pair:
 // <= 256 threads (two CTAs per SM) and <= 512 threads (one CTA per SM, twice the lines per
 // tile, i.e. twice as long contiguous runs on a strided side).
@@ -881,10 +1210,7 @@ cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   return launch_block_class<T, N, E, (THREADS > 512 ? THREADS : 512)>(sp, stream);
 }
 
-constexpr int points_per_thread(int n) {
-  // three passes at most: 64 -> 8*8, 128 -> 8*8*2, 256 -> 16*16, 512 -> 8*8*8, 1024 -> 16*16*4, ...
-  return (n == 64 || n == 128 || n == 512) ? 8 : 16;
-}
+int points_per_thread(int n) { return pow2_points_per_thread(n); }   // core.h: shared with the planner
 
 }  // namespace
 
@@ -905,6 +1231,7 @@ bool pow2_supported(const Stage &g, int L) {
 
 template <typename T>
 int pow2_pick_tile(const Stage &g, int L) {
+  if (g.ntile > 0) return g.ntile;   // explicit tile of a micro-blocked chain (the planner's choice)
   // Lines per tile.  Default: fill a 256-thread block (fp64) / 512-thread block (fp32): two
   // resident CTAs per SM in fp64, and a strided side then moves tl * sizeof(complex) = 64
   // contiguous bytes per point at N = 1024.  PFFT_B200_TL overrides (experiments).
@@ -938,6 +1265,19 @@ int pow2_pick_tile(const Stage &g, int L) {
 template <typename T>
 cudaError_t launch_stage_pow2(StageParams &sp, cudaStream_t stream) {
   if (sp.ntiles <= 0) return cudaSuccess;
+  if (sp.ntile > 0) {
+    // micro-blocked chain: tiles of 512 threads
+    switch (sp.L) {
+      case 64: return launch_blk_class<T, 64, 8, 512>(sp, stream);
+      case 128: return launch_blk_class<T, 128, 8, 512>(sp, stream);
+      case 256: return launch_blk_class<T, 256, 16, 512>(sp, stream);
+      case 512: return launch_blk_class<T, 512, 8, 512>(sp, stream);
+      case 1024: return launch_blk_class<T, 1024, 16, 512>(sp, stream);
+      case 2048: return launch_blk_class<T, 2048, 16, 512>(sp, stream);
+      case 4096: return launch_blk_class<T, 4096, 16, 512>(sp, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (sp.L) {
     case 64: return launch_variant<T, 64, 8>(sp, stream);
     case 128: return launch_variant<T, 128, 8>(sp, stream);
@@ -992,6 +1332,7 @@ void pow2_prepare(const Stage &g, StageParams &sp) {
   const bool seg_out = g.noseg > 1;
   if (seg_in && g.iblk % threads != 0) fast = false;
   if (seg_out && g.oblk % threads != 0) fast = false;
+  if (threads % g.iblk2 != 0 || threads % g.oblk2 != 0) fast = false;
   sp.fast = fast ? 1 : 0;
   static const int line_bars = [] {
     const char *e = getenv("PFFT_B200_LINEBAR");
@@ -1001,19 +1342,23 @@ void pow2_prepare(const Stage &g, StageParams &sp) {
   if (!fast) return;
   for (int e = 0; e < E; e++) {
     const long long idx = (long long)e * threads;
+    // (idx is a multiple of the micro-block sizes: only the high part moves)
+    auto along = [](long long x, long long blk2, long long blk2_stride, long long stride) {
+      return blk2 > 1 ? (x / blk2) * blk2_stride : x * stride;
+    };
     if (seg_in) {
       const long long seg = idx / g.iblk;
-      sp.in_off[e] = seg * g.iseg_stride + (idx - seg * g.iblk) * g.istride;
+      sp.in_off[e] = seg * g.iseg_stride + along(idx - seg * g.iblk, g.iblk2, g.iblk2_stride, g.istride);
     } else {
-      sp.in_off[e] = idx * g.istride;
+      sp.in_off[e] = along(idx, g.iblk2, g.iblk2_stride, g.istride);
     }
     if (seg_out) {
       const long long seg = idx / g.oblk;
       sp.out_seg[e] = (int)seg;
-      sp.out_off[e] = (idx - seg * g.oblk) * g.ostride;
+      sp.out_off[e] = along(idx - seg * g.oblk, g.oblk2, g.oblk2_stride, g.ostride);
     } else {
       sp.out_seg[e] = 0;
-      sp.out_off[e] = idx * g.ostride;
+      sp.out_off[e] = along(idx, g.oblk2, g.oblk2_stride, g.ostride);
     }
   }
 }

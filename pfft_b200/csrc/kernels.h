@@ -48,6 +48,10 @@ struct StageParams {
   int line_bars;             // per-line named barriers between passes (else CTA-wide)
   int ring_in, ring_out;     // fused pair: batch dimension 0 (the plane) wraps around a ring of this many slots
   const void *tw2, *tw3;     // per-pass twiddle tables [r-1][k]
+  // micro-blocked layouts / explicit tiles (core.h: Stage::iblk2 ...): handled by stage_blk_kernel
+  int iblk2, oblk2, ntile;
+  long long iblk2_stride, oblk2_stride;
+  long long tile_ioff[kMaxTile], tile_ooff[kMaxTile];
   long long in_off[16];      // element offset of line index e*THREADS on input
   long long out_off[16];     // ... on output, inside chunk out_seg[e]
   int out_seg[16];

@@ -131,6 +131,10 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     }
     if (g.in_elems == 0 && g.nin > 0) lines = 0;   // some batch extent of size 1 was dropped but another is 0
     sp.tile_dim = g.tile_dim;
+    sp.iblk2 = (int)g.iblk2; sp.iblk2_stride = g.iblk2_stride;
+    sp.oblk2 = (int)g.oblk2; sp.oblk2_stride = g.oblk2_stride;
+    sp.ntile = g.ntile;
+    for (int l = 0; l < g.ntile; l++) { sp.tile_ioff[l] = g.tile_ioff[l]; sp.tile_ooff[l] = g.tile_ooff[l]; }
     sp.in_real = g.in_real; sp.out_real = g.out_real; sp.conj_in = g.conj_in; sp.conj_out = g.conj_out;
     sp.mod_in = {g.mod_in.on, (int)g.mod_in.start, (int)g.mod_in.half, g.mod_in.extra};
     sp.mod_out = {g.mod_out.on, (int)g.mod_out.start, (int)g.mod_out.half, g.mod_out.extra};
@@ -148,6 +152,11 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
       sp.tiles_along = (g.batch[g.tile_dim].extent + tl - 1) / tl;
       sp.ntiles = others * sp.tiles_along;
     } else {
+      sp.tiles_along = 1;
+      sp.ntiles = lines;
+    }
+    if (g.ntile > 0) {
+      // explicit tiles: batch[] enumerates them (`lines` is their number here)
       sp.tiles_along = 1;
       sp.ntiles = lines;
     }
@@ -196,6 +205,10 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
         sp.tw2 = static_cast<const T *>(ts.dev) + 2 * ts.off2;
         sp.tw3 = static_cast<const T *>(ts.dev) + 2 * ts.off3;
         pow2_prepare<T>(g, sp);
+      }
+      if (g.ntile > 0 && !(fast && sp.fast)) {
+        *err = "internal: micro-blocked stage is not eligible for the register-resident kernel";
+        return false;
       }
     }
     pl->params.push_back(sp);
@@ -286,6 +299,7 @@ static void setup_fused_pair(PlanBase *pl) {
   if (!pl->use_pow2[i] || !pl->use_pow2[i + 1]) return;
   StageParams a = pl->params[i], b = pl->params[i + 1];
   if (!a.fast || !b.fast || a.L != b.L || a.sign != b.sign) return;
+  if (a.ntile > 0 || b.ntile > 0) return;   // micro-blocked chains have their own kernel
   if (sizeof(T) != 8) return;   // 8-byte cp.async is L1-cached (.ca): ring data written by other SMs could be stale
   if (ga.exchange >= 0 && s.exchanges[ga.exchange].nparts > 1) return;
   if (a.noseg != 1 || b.noseg != 1 || a.istride != 1 || b.istride != 1) return;

@@ -13,6 +13,7 @@
 // gathered innermost), and the stage after the exchange reads its lines straight
 // out of the received chunks.  No stand-alone pack / unpack / transpose pass exists.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <sstream>
@@ -34,15 +35,29 @@ struct Layout {
   int seg_dim = -1;          // dimension delivered in chunks by an exchange
   INT seg_blk = 0, seg_stride = 0;
   bool real = false;
+  // micro-blocking: index x of dim t sits at (x / mb[t]) * stride[t] + (x % mb[t]) * lstride[t]; the low
+  // parts of all blocked dims form one dense block (dims `border`, outer -> inner) that is the
+  // innermost unit of the layout.  mb == 1: plain (lstride == stride).
+  INT mb[kMaxDims + 1] = {1, 1, 1, 1, 1, 1, 1, 1, 1};
+  INT lstride[kMaxDims + 1] = {0};
+  int border[kMaxDims + 1] = {0};
+  int nbord = 0;
 
   void finish() {
     INT s = 1;
+    for (int k = nbord - 1; k >= 0; k--) {
+      lstride[border[k]] = s;
+      s *= mb[border[k]];
+    }
     for (int k = nord - 1; k >= 0; k--) {
-      stride[order[k]] = s;
-      s *= pitch[order[k]];
+      const int t = order[k];
+      stride[t] = s;
+      if (mb[t] == 1) lstride[t] = s;
+      s *= pitch[t] / mb[t];
     }
     total = s;
   }
+  bool blocked() const { return nbord > 0; }
 };
 
 struct HalfSizes {        // sizes one half of the schedule works with (physical units on complex sides)
@@ -73,6 +88,10 @@ struct Builder {
   INT iblk[kMaxMesh], mblk[kMaxMesh], oblk[kMaxMesh];
   HalfSizes hs[2];
   INT cur_ext[kMaxDims + 1];   // current local extents (complex-physical / real as stored)
+  // micro-blocked intermediate layouts (plan_microblocks): tile factor of step s along dim t
+  bool mbk = false;
+  int mbk_order = 1;           // 1: [others][gather][split] (producer writes contiguously), 2: [others][split][gather]
+  INT tilef[2 * kMaxDims + 4][kMaxDims + 1];
 
   Builder(const Problem &pp, Schedule &ss) : p(pp), s(ss) {}
 
@@ -223,7 +242,7 @@ struct Builder {
   // ---- one stage ------------------------------------------------------------------
   // Lin/Lout carry extents of every dimension; along `a` Lin.ext = elements present, Lout.ext = kept.
   void emit(const Step &st, const Layout &Lin, const Layout &Lout, const HalfSizes &h, bool first, bool last,
-            int noseg, const INT *seg_rows) {
+            int noseg, const INT *seg_rows, const INT *Fs = nullptr) {
     Stage g;
     const int a = st.dim;
     const bool do_trafo = st.trafo && !user_skip(a);
@@ -289,7 +308,11 @@ struct Builder {
       return;
     }
     // fft-dim addressing
-    g.istride = Lin.stride[a];
+    g.istride = Lin.lstride[a];
+    if (Lin.mb[a] > 1) {
+      g.iblk2 = Lin.mb[a];
+      g.iblk2_stride = Lin.stride[a];
+    }
     if (Lin.seg_dim == a) {
       g.iblk = Lin.seg_blk;
       g.iseg_stride = Lin.seg_stride;
@@ -297,13 +320,18 @@ struct Builder {
       g.iblk = std::max<INT>(g.nin, 1);
       g.iseg_stride = 0;
     }
-    g.ostride = Lout.stride[a];
+    g.ostride = Lout.lstride[a];
+    if (Lout.mb[a] > 1) {
+      g.oblk2 = Lout.mb[a];
+      g.oblk2_stride = Lout.stride[a];
+    }
     if (noseg > 0) {
       g.noseg = noseg;
       g.oblk = st.split_blk;
       INT off = 0;
       for (int q = 0; q < noseg; q++) {
-        g.oseg_cnt[q] = noseg == 1 ? Lout.total : seg_rows[q] * Lout.stride[a];
+        // (a micro-blocked chunk layout describes ONE chunk; all chunks are equal then)
+        g.oseg_cnt[q] = (noseg == 1 || Lout.blocked()) ? Lout.total : seg_rows[q] * Lout.stride[a];
         g.oseg_off[q] = off;
         off += g.oseg_cnt[q];
       }
@@ -314,13 +342,46 @@ struct Builder {
     }
     // batch dims: everything except `a`, merged where both layouts allow
     std::vector<BatchDim> b;
+    struct TileDim { INT f, ils, ols; };
+    std::vector<TileDim> td;
     INT lines = 1;
     for (int k = 0; k < Lin.nord; k++) {
       int t = Lin.order[k];
       if (t == a) continue;
       lines *= Lin.ext[t];
       if (Lin.ext[t] == 1) continue;
-      b.push_back({Lin.ext[t], Lin.stride[t], Lout.stride[t], t == kTuple ? -1 : t});
+      const INT f = Fs ? Fs[t] : 1, mi = Lin.mb[t], mo = Lout.mb[t];
+      if (f == 1) {
+        if (mi != 1 || mo != 1) { s.error = "internal: micro-blocked dimension outside the tile"; return; }
+        b.push_back({Lin.ext[t], Lin.stride[t], Lout.stride[t], t == kTuple ? -1 : t});
+        continue;
+      }
+      // the low part (x % f) selects the line inside the tile, the high part enumerates tiles
+      if ((mi != 1 && mi != f) || (mo != 1 && mo != f) || Lin.ext[t] % f) { s.error = "internal: tile / micro-block mismatch"; return; }
+      td.push_back({f, Lin.lstride[t], Lout.lstride[t]});
+      if (Lin.ext[t] / f > 1)
+        b.push_back({Lin.ext[t] / f, mi == f ? Lin.stride[t] : f * Lin.stride[t], mo == f ? Lout.stride[t] : f * Lout.stride[t], t});
+    }
+    if (!td.empty()) {
+      // line order inside the tile: fastest along the smallest low stride of the blocked side, so that a
+      // warp that walks lines first touches consecutive addresses there
+      const bool by_out = Lout.blocked();
+      std::sort(td.begin(), td.end(), [&](const TileDim &x, const TileDim &y) { return by_out ? x.ols > y.ols : x.ils > y.ils; });
+      INT nt = 1;
+      for (auto &x : td) nt *= x.f;
+      if (nt > kMaxTile) { s.error = "internal: tile too large"; return; }
+      g.ntile = (int)nt;
+      for (INT l = 0; l < nt; l++) {
+        INT rest = l, io = 0, oo = 0;
+        for (int q = (int)td.size() - 1; q >= 0; q--) {
+          const INT c = rest % td[q].f;
+          rest /= td[q].f;
+          io += c * td[q].ils;
+          oo += c * td[q].ols;
+        }
+        g.tile_ioff[l] = io;
+        g.tile_ooff[l] = oo;
+      }
     }
     bool merged = true;
     while (merged) {
@@ -357,6 +418,7 @@ struct Builder {
       if (g.ostride != 1) g.tile_dim = pick(true);
       else g.tile_dim = pick(false);
     }
+    if (g.ntile > 0) g.tile_dim = -1;
     g.in_elems = lines * g.nin;
     g.out_elems = lines * g.nout;
     s.stages.push_back(g);
@@ -399,6 +461,74 @@ struct Builder {
     L.real = real;
     L.finish();
     return L;
+  }
+
+  // ---- micro-blocked intermediate layouts ------------------------------------------------
+  // Measured on B200 (profiles/microbench/runlen.cu): a pass whose strided side moves 128-byte
+  // runs reaches 83 % of the contiguous rate (70 % with runs on both sides), 256-byte runs and
+  // longer reach 99 %.  A tile of tl lines x L points can only offer tl-element runs to a plain
+  // [k][...] layout, so for chains of register-resident power-of-two stages the boundary between
+  // stage s and s+1 is stored as dense blocks  [A lo][O lo][G lo]  (A: dimension stage s
+  // transformed, G: the one stage s+1 transforms, O: the others) and the tiles of both stages
+  // are 2-D: stage s takes (G lo x O lo) lines, stage s+1 takes (A lo x O lo).  Producer tile and
+  // consumer tile then share a whole block (tA * tO * tG elements, 512 / 256 bytes at 1024^3 fp64).
+  // All ranks must agree, hence only global quantities enter the decision.
+  void plan_microblocks(const std::vector<Step> &steps) {
+    mbk = false;
+    const char *env = getenv("PFFT_B200_BLOCKED");
+    const int mode = env ? atoi(env) : 1;
+    if (mode <= 0) return;
+    mbk_order = mode == 2 ? 2 : 1;
+    if (p.kind != Kind::C2C || p.howmany != 1 || m3.active || d != r + 1 || d < 2) return;
+    if (tr != F_TRANSPOSED_IN && tr != F_TRANSPOSED_OUT) return;
+    if ((int)steps.size() != d || p.has_skip || p.has_iblock || p.has_oblock) return;
+    if (p.flags & (F_SHIFTED_IN | F_SHIFTED_OUT)) return;
+    int tl = 0;
+    for (int t = 0; t < d; t++) {
+      const INT L = p.n[t];
+      if (p.ni[t] != L || p.no[t] != L || L < 64 || L > 1024 || (L & (L - 1))) return;   // (longer lines: staging + exchange buffers exceed shared memory)
+      const int lines = 512 / pow2_threads_per_line((int)L);
+      if (tl == 0) tl = lines;
+      if (lines != tl) return;
+    }
+    if (tl < 2 || tl > kMaxTile) return;
+    // the tile's lines are spread over ALL dimensions the first stage does not transform, the larger
+    // factors on the dimensions transformed first: every boundary then gets blocks of tl * tG elements
+    int bits = 0;
+    while ((1 << bits) < tl) bits++;
+    INT fac[kMaxDims];
+    INT fmax = 1;
+    for (int q = 0; q < d - 1; q++) {
+      fac[q] = (INT)1 << (bits / (d - 1) + (q < bits % (d - 1) ? 1 : 0));
+      if (fac[q] < 2) return;
+      fmax = std::max(fmax, fac[q]);
+    }
+    for (int t = 0; t < d; t++)
+      for (int m = 0; m < r; m++) {
+        if (p.n[t] % ((INT)np[m] * fmax)) return;                                      // whole blocks on every rank
+        if ((p.n[t] / np[m]) % pow2_threads_per_line((int)p.n[t])) return;             // chunk boundaries on thread boundaries
+      }
+    for (size_t i = 0; i < steps.size(); i++) {
+      if (!steps[i].trafo) return;
+      if ((i + 1 < steps.size()) != (steps[i].xch_mesh >= 0)) return;
+      for (int t = 0; t <= kMaxDims; t++) tilef[i][t] = 1;
+    }
+    // first stage: factors in the order in which the dimensions will be transformed
+    for (size_t i = 0; i + 1 < steps.size(); i++) {
+      if (steps[i].xch_gather != steps[i + 1].dim) return;
+      tilef[0][steps[i].xch_gather] = fac[i];
+    }
+    // a stage inherits its predecessor's tile with the factor of its own dimension moved to the
+    // dimension the predecessor transformed
+    for (size_t i = 0; i + 1 < steps.size(); i++) {
+      const Step &st = steps[i];
+      if (st.dim != st.xch_split || steps[i + 1].dim != st.xch_gather) return;
+      for (int t = 0; t <= kMaxDims; t++) tilef[i + 1][t] = tilef[i][t];
+      tilef[i + 1][st.xch_split] = tilef[i][st.xch_gather];
+      tilef[i + 1][st.xch_gather] = 1;
+      if (tilef[i][st.xch_gather] < 2) return;     // (blocks of at least tl * 2 elements on both sides)
+    }
+    mbk = true;
   }
 
   bool build() {
@@ -508,6 +638,8 @@ struct Builder {
       return false;
     }
 
+    plan_microblocks(steps);
+
     // ---- walk the steps, tracking the layout
     Layout cur = user_layout(true);
     for (int t = 0; t < d; t++) cur_ext[t] = cur.ext[t];
@@ -574,7 +706,34 @@ struct Builder {
             mode = 1;
           }
         }
+        if (mbk) {
+          // outer order: everything but the pair first, then [gather][split] (the producing tile writes one
+          // contiguous piece per destination) or [split][gather] (the consuming tile reads one)
+          int k = 0;
+          for (int t = 0; t <= r; t++)
+            if (t != st.xch_split && t != st.xch_gather) ord[k++] = t;
+          ord[k++] = mbk_order == 1 ? st.xch_gather : st.xch_split;
+          ord[k++] = mbk_order == 1 ? st.xch_split : st.xch_gather;
+          mode = 2;
+        }
         Lout = chunk_layout(st.xch_split, st.xch_gather, st.gather_blk, out_real, mode, ord);
+        if (mbk) {
+          // one chunk = the rows of one destination (uniform by construction)
+          Lout.pitch[st.xch_split] = st.split_blk;
+          const INT *Fp = tilef[i], *Fc = tilef[i + 1];
+          Lout.nbord = 0;
+          auto add = [&](int t, INT f) {
+            Lout.mb[t] = f;
+            if (f > 1) Lout.border[Lout.nbord++] = t;
+          };
+          add(st.xch_split, Fc[st.xch_split]);
+          for (int t = 0; t <= r; t++)
+            if (t != st.xch_split && t != st.xch_gather) {
+              if (Fp[t] != Fc[t]) { s.error = "internal: tile factors of neighbouring stages differ"; return false; }
+              add(t, Fp[t]);
+            }
+          add(st.xch_gather, Fp[st.xch_gather]);
+        }
         Lout.finish();
         noseg = np[m];
         for (int q = 0; q < noseg; q++) seg_rows[q] = block_extent(st.split_n, st.split_blk, q);
@@ -592,7 +751,7 @@ struct Builder {
         // real rows may be padded (PFFT_PADDED_C2R): extent kept is `no`, pitch is the user's row length
         Lout.ext[a] = out_ext;
       }
-      emit(st, Lin, Lout, h, first, last, noseg, seg_rows);
+      emit(st, Lin, Lout, h, first, last, noseg, seg_rows, mbk ? tilef[i] : nullptr);
       if (!s.error.empty()) return false;
       Stage &g = s.stages.back();
 
@@ -651,6 +810,11 @@ struct Builder {
 
 }  // namespace
 
+int pow2_points_per_thread(int L) {
+  // three radix passes at most: 64 -> 8*8, 128 -> 8*8*2, 256 -> 16*16, 512 -> 8*8*8, 1024 -> 16*16*4, ...
+  return (L == 64 || L == 128 || L == 512) ? 8 : 16;
+}
+
 bool build_schedule(const Problem &p, int pid, Schedule *sched) {
   sched->prob = p;
   sched->pid = pid;
@@ -701,7 +865,12 @@ std::string schedule_to_json(const Schedule &s) {
       << ",\"dim\":" << g.dim << ",\"n\":" << g.n << ",\"nin\":" << g.nin << ",\"zin\":" << g.zin
       << ",\"nout\":" << g.nout << ",\"zout\":" << g.zout << ",\"istride\":" << g.istride
       << ",\"iblk\":" << g.iblk << ",\"iseg_stride\":" << g.iseg_stride << ",\"ostride\":" << g.ostride
-      << ",\"oblk\":" << g.oblk << ",\"noseg\":" << g.noseg << ",\"oseg_off\":";
+      << ",\"oblk\":" << g.oblk << ",\"noseg\":" << g.noseg << ",\"iblk2\":" << g.iblk2 << ",\"iblk2_stride\":" << g.iblk2_stride
+      << ",\"oblk2\":" << g.oblk2 << ",\"oblk2_stride\":" << g.oblk2_stride << ",\"ntile\":" << g.ntile << ",\"tile_ioff\":";
+    arr(g.tile_ioff, g.ntile);
+    o << ",\"tile_ooff\":";
+    arr(g.tile_ooff, g.ntile);
+    o << ",\"oseg_off\":";
     arr(g.oseg_off, g.noseg);
     o << ",\"oseg_cnt\":";
     arr(g.oseg_cnt, g.noseg);

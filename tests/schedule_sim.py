@@ -76,6 +76,10 @@ def run_stage(g, inbuf):
     if any(b[0] == 0 for b in g["batch"]):
         lin = lin[:0]
         lout = lout[:0]
+    if g.get("ntile", 0) > 0:
+        # explicit tiles (micro-blocked layouts): batch[] enumerates tiles, the tables place the lines of a tile
+        lin = (lin[:, None] + np.asarray(g["tile_ioff"], dtype=np.int64)[None, :]).reshape(-1)
+        lout = (lout[:, None] + np.asarray(g["tile_ooff"], dtype=np.int64)[None, :]).reshape(-1)
     out_dtype = np.float64 if g["out_real"] else np.complex128
     chunks = [np.zeros(c, dtype=out_dtype) for c in g["oseg_cnt"]]
     nin, n, nout = g["nin"], g["n"], g["nout"]
@@ -83,7 +87,9 @@ def run_stage(g, inbuf):
         return chunks
     j = np.arange(nin, dtype=np.int64)
     seg = j // g["iblk"]
-    in_idx = seg * g["iseg_stride"] + (j - seg * g["iblk"]) * g["istride"]
+    jl = j - seg * g["iblk"]
+    b2 = g.get("iblk2", 1)
+    in_idx = seg * g["iseg_stride"] + (jl * g["istride"] if b2 == 1 else (jl // b2) * g["iblk2_stride"] + (jl % b2) * g["istride"])
     X = inbuf[lin[:, None] + in_idx[None, :]]
     if g["conj_in"]:
         X = np.conj(X)
@@ -121,7 +127,9 @@ def run_stage(g, inbuf):
         ks = k[kseg == q]
         if ks.size == 0:
             continue
-        pos = lout[:, None] + ((ks - q * g["oblk"]) * g["ostride"])[None, :]
+        kl = ks - q * g["oblk"]
+        b2 = g.get("oblk2", 1)
+        pos = lout[:, None] + (kl * g["ostride"] if b2 == 1 else (kl // b2) * g["oblk2_stride"] + (kl % b2) * g["ostride"])[None, :]
         chunks[q][pos] = Y[:, ks]
     return chunks
 

@@ -128,6 +128,11 @@ MULTI_RANK = [
     dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_IN, sign=+1),
     dict(kind="r2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
     dict(kind="c2c", n=[64, 64, 64], np=[1, 2, 4], flags=T_OUT),
+    # micro-blocked chains of power-of-two stages across exchanges
+    dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_OUT, tag="-blk"),
+    dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_IN, sign=+1, tag="-blk"),
+    dict(kind="c2c", n=[128, 128, 128], np=[2, 4], flags=T_OUT, tag="-blk"),
+    dict(kind="c2c", n=[64, 64, 64], np=[4, 1], flags=T_OUT, precision="single", tag="-blk"),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
     dict(kind="r2r", n=[7, 6, 5, 4], np=[2, 2, 2], kinds=[po.REDFT10, po.RODFT00, po.REDFT00, po.RODFT01], flags=T_OUT),
@@ -193,6 +198,44 @@ def test_reference_round_trip_baseline_size(world):
     """BASELINE configs[1] shape on one GPU: 512^3 c2c fp64, TRANSPOSED_OUT / TRANSPOSED_IN."""
     err = _round_trip(world, [512, 512, 512], [1, 1], T_OUT, T_IN)
     assert err < 1e-12, err
+
+
+@pytest.mark.parametrize("n,dtype,tol", [([512, 512, 512], "float64", 1e-12), ([512, 1024, 512], "float64", 1e-12),
+                                         ([256, 256, 256], "float64", 1e-12), ([512, 512, 512], "float32", 2e-5)])
+def test_forward_values_at_baseline_size(world, n, dtype, tol):
+    """BASELINE-size forward output, element by element, against a library FFT of the same array
+    (torch.fft = cuFFT, used here ONLY as a second checker where the numpy oracle takes minutes);
+    TRANSPOSED_OUT layout [k1][k2][k0].  Covers the 8-line micro-blocked tiles of the headline size."""
+    import torch
+    pf = world
+    rdt = getattr(torch, dtype)
+    cdt = torch.complex128 if dtype == "float64" else torch.complex64
+    comm = pf.create_procmesh([1, 1])
+    N = int(np.prod(n))
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.rand(N, 2, dtype=rdt, device="cuda", generator=g) * 2 - 1
+    X = torch.empty_like(x)
+    npdt = np.complex128 if dtype == "float64" else np.complex64
+    plan = pf.plan_dft(n, x, X, comm, pf.FORWARD, T_OUT, dtype=npdt)
+    assert plan is not None, pf.last_error()
+    plan.execute(x, X)
+    want = torch.fft.fftn(torch.view_as_complex(x).reshape(n)).permute(1, 2, 0).contiguous()
+    got = torch.view_as_complex(X).reshape(n[1], n[2], n[0])
+    err = ((got - want).abs().max() / want.abs().max()).item()
+    del want
+    # and back through TRANSPOSED_IN
+    y = torch.empty_like(x)
+    back = pf.plan_dft(n, X, y, comm, pf.BACKWARD, T_IN, dtype=npdt)
+    back.execute(X, y)
+    err_rt = ((y / N - x).abs().max()).item()
+    plan.destroy(); back.destroy(); comm.free()
+    assert err < tol and err_rt < 10 * tol, (err, err_rt)
+    assert all(k == "pow2" for k in plan_kernels(pf, n))
+
+
+def plan_kernels(pf, n):
+    s = pf.describe_schedule("c2c", n, [1, 1], 0, T_OUT)
+    return ["pow2" if g["ntile"] > 0 else "plain" for g in s["stages"]]
 
 
 def test_linearity_and_parseval_at_size(world):

@@ -92,6 +92,15 @@ CASES = [
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
     dict(kind="c2c", n=[8, 8, 8], np=[1, 1, 1]),
+    # chains of register-resident power-of-two stages: micro-blocked intermediate layouts, 2-D tiles
+    dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_OUT),
+    dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_OUT),
+    dict(kind="c2c", n=[64, 64, 64], np=[2, 4], flags=T_IN, sign=+1),
+    dict(kind="c2c", n=[64, 64, 64], np=[4, 1], flags=T_OUT),
+    dict(kind="c2c", n=[128, 128, 128], np=[1, 2], flags=T_OUT),
+    dict(kind="c2c", n=[64, 64, 64, 64], np=[2, 1, 2], flags=T_OUT),
+    dict(kind="c2c", n=[64, 64], np=[2], flags=T_OUT),
     # r2r (reference tests/simple_check_r2r*.c)
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.REDFT00, po.REDFT01, po.REDFT10]),
     dict(kind="r2r", n=[13, 11, 9], np=[2, 2], kinds=[po.RODFT00, po.RODFT10, po.REDFT11], flags=T_OUT),
@@ -122,6 +131,24 @@ def test_transposed_out_has_no_extra_passes(built_lib):
     # headline config: every chunk of the first exchange is 512 MiB of complex doubles
     assert s["exchanges"][0]["send_cnt"] == [512 * 256 * 256] * 4
     assert s["exchanges"][1]["send_cnt"] == [512 * 256 * 512] * 2
+
+
+def test_power_of_two_chains_use_micro_blocked_layouts(built_lib):
+    """Headline config: 8-line tiles as 4 x 2 lines; producer and consumer tiles share 512- / 256-byte blocks."""
+    for flags in (T_OUT, T_IN):
+        s = pf.describe_schedule("c2c", [1024, 1024, 1024], [2, 4], 5, flags)
+        assert s["error"] == ""
+        g0, g1, g2 = s["stages"]
+        assert [g["ntile"] for g in s["stages"]] == [8, 8, 8]
+        assert (g0["oblk2"], g1["iblk2"], g1["oblk2"], g2["iblk2"]) == (4, 4, 2, 2)
+        assert g0["iblk2"] == 1 and g2["oblk2"] == 1 and g0["istride"] == 1 and g2["ostride"] == 1
+        assert g0["tile_ooff"] == list(range(8)) and g1["tile_ioff"] == [4 * l for l in range(8)]
+        assert g1["tile_ooff"] == list(range(8)) and g2["tile_ioff"] == [2 * l for l in range(8)]
+        # exchanges still move exactly the reference's chunk sizes
+        assert s["exchanges"][0]["send_cnt"] == ([512 * 256 * 256] * 4 if flags == T_OUT else [512 * 256 * 512] * 2)
+    # ragged or non-power-of-two sizes keep the plain layouts
+    assert all(g["ntile"] == 0 for g in pf.describe_schedule("c2c", [1024, 1000, 1024], [2, 4], 0, T_OUT)["stages"])
+    assert all(g["ntile"] == 0 for g in pf.describe_schedule("c2c", [1024, 1024, 1024], [3, 2], 0, T_OUT)["stages"])
 
 
 def test_illegal_combinations_are_refused(built_lib):
