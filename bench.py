@@ -247,6 +247,29 @@ def main():
                                 for k, v in by_kernel.items()},
                 "stage_ms_forward": [sum(r[i] for r in stage_ms_f) / len(stage_ms_f) for i in range(len(stage_ms_f[0]))],
                 "stage_ms_backward": [sum(r[i] for r in stage_ms_b) / len(stage_ms_b) for i in range(len(stage_ms_b[0]))]}
+    # ---- HBM + NVLink roofline of the whole transform: per GPU and per transform
+    # HBM bytes = 2 * d * 16 B * N / P, NVLink bytes (one direction) = sum over mesh dims of (16 B * N / P) * (P_d - 1) / P_d
+    nvl_peak = 900.0          # GB/s per direction, NVLink 5 nominal; SM stores measured 707, copy engine 781 (profiles/microbench)
+    hbm_bytes = 3 * alg_pass
+    nvl_bytes = sum(16.0 * local_elems * (pd - 1) / pd for pd in mesh)
+    t_hbm = hbm_bytes / (peak * 1e9) * 1e3
+    t_nvl = nvl_bytes / (nvl_peak * 1e9) * 1e3
+    t_transform = ms_per_step / 2
+    combined = {"hbm_bytes_per_gpu": hbm_bytes, "nvlink_bytes_per_gpu": nvl_bytes, "hbm_peak_gbs": peak,
+                "nvlink_peak_gbs": nvl_peak, "t_hbm_ms": t_hbm, "t_nvlink_ms": t_nvl,
+                "t_roof_serial_ms": t_hbm + t_nvl, "t_roof_overlap_ms": max(t_hbm, t_nvl),
+                "t_measured_ms": t_transform, "frac_of_serial_roofline": (t_hbm + t_nvl) / t_transform,
+                "nvlink_gbs_in_exchange_stages": None}
+    if world > 1:
+        # stages in front of a real exchange push their remote chunks over NVLink inside the kernel
+        rates = []
+        fm = roofline_stage = [sum(r[i] for r in stage_ms_f) / len(stage_ms_f) for i in range(len(stage_ms_f[0]))]
+        k = 0
+        for pd in reversed(mesh):          # forward: first exchange over the last mesh dimension
+            if pd > 1 and k < len(fm) and fm[k] > 0:
+                rates.append(16.0 * local_elems * (pd - 1) / pd / (fm[k] * 1e-3) / 1e9)
+            k += 1
+        combined["nvlink_gbs_in_exchange_stages"] = rates
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -291,7 +314,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "roundtrip_rel_err": rel, "clocks": clk.summary(), "gpu_launches": launches,
-                "roofline": roofline, "transport": desc["transport"]}
+                "roofline": roofline, "roofline_hbm_nvlink": combined, "transport": desc["transport"]}
         if e2e:
             line["e2e"] = e2e
         if cpu:

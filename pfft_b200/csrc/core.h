@@ -114,6 +114,13 @@ struct Stage {
   INT oblk2 = 1, oblk2_stride = 0;
   int ntile = 0;
   INT tile_ioff[kMaxTile] = {0}, tile_ooff[kMaxTile] = {0};
+  // Bank swizzle baked into the blocked layout: inside block b (index along the gathered dimension) the
+  // lines are permuted, so that a consumer reading `iblk2` words out of each of several consecutive
+  // blocks (dense in shared memory) hits different banks.  Consumer: line l of the tile sits at
+  // tile_ioff[l] ^ ((b & iswz_mask) * iblk2), b = (index inside the segment) / iblk2.  Producer: in a tile
+  // whose batch coordinate oswz_batch is c, line l goes to tile_ooff[l] ^ ((c & oswz_mask) << oswz_shift).
+  int iswz_mask = 0;
+  int oswz_mask = 0, oswz_shift = 0, oswz_batch = -1;
   bool in_real = false, out_real = false;
   bool conj_in = false, conj_out = false;
   SignMod mod_in, mod_out;

@@ -910,30 +910,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned byt
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
 }
 
-// Geometry of the staging buffer, shared by the kernel and its launcher.
-//  line-major input: lines are dense (pitch N), fetched in pieces of <= 2 KB;
-//  blocked input: one piece per micro-block, kept dense, blocks padded by one line-piece so that the
-//  strided reads of a line (tG words out of every block) fall into different banks.
+// Geometry of the staging buffer, shared by the kernel and its launcher.  The tile's input is a few
+// contiguous pieces of global memory -- its lines (line-major input) or, for a micro-blocked input, the
+// blocks coming from one source rank (tl * iblk words: blocks are contiguous along the gathered
+// dimension) -- copied densely, piece after piece, in chunks of <= 4 KB by the first `nchunks` threads.
 struct StageGeom {
-  int blocked, nchunks, chunk_elems, pitch;   // pitch: of a line (line-major) / of a block (blocked), in complex words
-  long long words;                            // complex words of the staging buffer
+  int blocked, nchunks, chunk_elems, piece_elems;
 };
-__host__ __device__ inline StageGeom stage_geom(int N, int tl, int iblk2, int elem_bytes) {
+__host__ __device__ inline StageGeom stage_geom(int N, int tl, int iblk2, long long iblk, long long iseg_stride, int elem_bytes) {
   StageGeom g;
   g.blocked = iblk2 > 1;
-  if (g.blocked) {
-    g.chunk_elems = tl * iblk2;
-    g.nchunks = N / iblk2;
-    g.pitch = g.chunk_elems + iblk2;
-    g.words = (long long)g.nchunks * g.pitch;
-  } else {
-    int cpl = N * elem_bytes / 2048;
-    if (cpl < 1) cpl = 1;
-    g.chunk_elems = N / cpl;
-    g.nchunks = tl * cpl;
-    g.pitch = N;
-    g.words = (long long)tl * N;
-  }
+  g.piece_elems = g.blocked ? tl * (int)(iseg_stride ? iblk : N) : N;
+  g.chunk_elems = 4096 / elem_bytes;
+  if (g.chunk_elems > g.piece_elems) g.chunk_elems = g.piece_elems;
+  g.nchunks = tl * N / g.chunk_elems;
   return g;
 }
 
@@ -945,18 +935,17 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
   constexpr bool SPLIT = sizeof(T) == 8;                 // exchange real and imaginary parts separately
   using XE = typename std::conditional<SPLIT, T, cx<T>>::type;   // 8-byte exchange word
   static_assert(sizeof(XE) == 8, "exchange words are 8 bytes");
-  // the last radix-4 pass of N = 1024 keeps w^k and w^2k in shared memory and multiplies them for w^3k
-  constexpr bool W3MUL = P::NPASS == 3 && P::R3 == 4;
+  constexpr bool W3MUL = false;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tl = sp.tl;
-  const StageGeom sg = stage_geom(N, tl, sp.iblk2, (int)sizeof(cx<T>));
+  const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, (int)sizeof(cx<T>));
   // exchange buffer: lines of a tile must fall into different banks for the tile-minor gathers
   // (8 lines x 2 x 8-byte words per half-warp: pitch = 2 mod 16)
   const int pitch_x = N + (N >> 4) + 2;
   cx<T> *stage = reinterpret_cast<cx<T> *>(smem_raw);
-  XE *xbuf = reinterpret_cast<XE *>(stage + sg.words);
+  XE *xbuf = reinterpret_cast<XE *>(stage + (size_t)tl * N);
   constexpr int TW2 = (P::R2 - 1) * P::R1;
-  constexpr int TW3 = P::NPASS == 3 ? ((W3MUL ? 2 : P::R3 - 1)) * P::R1 * P::R2 : 0;
+  constexpr int TW3 = P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0;
   cx<T> *tw_s = reinterpret_cast<cx<T> *>(xbuf + (size_t)tl * pitch_x);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(tw_s + TW2 + TW3);
   const int tid = threadIdx.x;
@@ -988,8 +977,11 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
   const cx<T> *my_first;
   int my_step;
   if (sg.blocked) {
-    my_first = stage + (t_c / sp.iblk2) * sg.pitch + (int)sp.tile_ioff[tt_c] + (t_c % sp.iblk2);
-    my_step = (THREADS / sp.iblk2) * sg.pitch;
+    // block j / tG of the tile, my line's words inside it (lines are XOR-permuted from block to block:
+    // a quarter-warp reads 8 / tG consecutive blocks and must hit different banks)
+    const int b = t_c / sp.iblk2, bk = tl * sp.iblk2;
+    my_first = stage + b * bk + ((int)sp.tile_ioff[tt_c] ^ ((b & sp.iswz_mask) * sp.iblk2)) + (t_c % sp.iblk2);
+    my_step = (THREADS / sp.iblk2) * bk;
   } else {
     my_first = stage + tt_c * N + t_c;
     my_step = THREADS;
@@ -1004,25 +996,20 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
   const cx<T> *chunk_src = reinterpret_cast<const cx<T> *>(sp.in);
   unsigned chunk_dst = (unsigned)__cvta_generic_to_shared(stage);
   if (loader) {
-    if (sg.blocked) {
-      const long long j0 = (long long)tid * sp.iblk2;             // first line index of block `tid`
-      const long long seg = sp.iseg_stride ? j0 / sp.iblk : 0;
-      chunk_src += seg * sp.iseg_stride + ((j0 - seg * sp.iblk) / sp.iblk2) * sp.iblk2_stride;
-      chunk_dst += (unsigned)(tid * sg.pitch * sizeof(cx<T>));
-    } else {
-      const int cpl = sg.nchunks / tl, l = tid / cpl, part = tid % cpl;
-      chunk_src += sp.tile_ioff[l] + (long long)part * sg.chunk_elems;
-      chunk_dst += (unsigned)((l * N + part * sg.chunk_elems) * sizeof(cx<T>));
-    }
+    const int first = tid * sg.chunk_elems, q = first / sg.piece_elems, within = first % sg.piece_elems;
+    chunk_src += (sg.blocked ? (long long)q * sp.iseg_stride : sp.tile_ioff[q]) + within;
+    chunk_dst += (unsigned)(first * sizeof(cx<T>));
   }
-  const long long out_thread = sp.tile_ooff[tt_s] +
-                               (out_lm ? (long long)t_s * sp.ostride
-                                       : (long long)(t_s / sp.oblk2) * sp.oblk2_stride + (long long)(t_s % sp.oblk2) * sp.ostride);
+  const long long out_line = sp.tile_ooff[tt_s];
+  const long long out_point = out_lm ? (long long)t_s * sp.ostride
+                                     : (long long)(t_s / sp.oblk2) * sp.oblk2_stride + (long long)(t_s % sp.oblk2) * sp.ostride;
   const unsigned ntiles = (unsigned)sp.ntiles;
+  // obase includes this thread's line: its place inside the output blocks depends on the tile (bank swizzle)
   auto locate = [&](unsigned tile, long long &ibase, long long &obase) {
     unsigned rest = tile;
     ibase = 0;
     obase = 0;
+    unsigned cswz = 0;
 #pragma unroll
     for (int k = kMaxBatch - 1; k >= 0; k--) {
       if (k >= sp.nbatch) continue;
@@ -1031,7 +1018,9 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
       rest /= ext;
       ibase += (long long)c * sp.bis[k];
       obase += (long long)c * sp.bos[k];
+      if (k == sp.oswz_batch) cswz = c;
     }
+    obase += out_line ^ (long long)((cswz & (unsigned)sp.oswz_mask) << sp.oswz_shift);
   };
   auto prefetch = [&](long long ibase) {
     if (tid == 0) mbar_arrive_expect_tx(bar_full, tile_bytes);
@@ -1100,14 +1089,13 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
       pass_regs<T, N, E, P::R2, P::R1, false>(x, t_s, tw2);
     }
 #undef PFB_EXCHANGE
-    const long long thread_off = obase_cur + out_thread;
+    const long long thread_off = obase_cur + out_point;
 #pragma unroll
     for (int e = 0; e < E; e++) {
       V raw;
       raw.x = BWD ? x[e].y : x[e].x;
       raw.y = BWD ? x[e].x : x[e].y;
-      cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[sp.out_seg[e]]) + thread_off + sp.out_off[e];
-      *reinterpret_cast<V *>(out) = raw;
+      *reinterpret_cast<V *>(reinterpret_cast<cx<T> *>(sp.outp[e]) + thread_off) = raw;
     }
   }
 }
@@ -1116,12 +1104,15 @@ template <typename T, int N, int E, int MAXT>
 cudaError_t launch_blk_class(StageParams &sp, cudaStream_t stream) {
   constexpr int THREADS = N / E;
   using P = Passes<N, E>;
-  constexpr bool W3MUL = P::NPASS == 3 && P::R3 == 4;
-  constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (W3MUL ? 2 : P::R3 - 1) * P::R1 * P::R2 : 0);
+  constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const int tl = sp.tl;
-  const StageGeom sg = stage_geom(N, tl, sp.iblk2, 2 * (int)sizeof(T));
+  const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, 2 * (int)sizeof(T));
   const size_t pitch_x = N + (N >> 4) + 2;
-  const size_t smem = (size_t)sg.words * 2 * sizeof(T) + tl * pitch_x * 8 + (size_t)TWN * 2 * sizeof(T) + 16;
+  const size_t smem = (size_t)tl * N * 2 * sizeof(T) + tl * pitch_x * 8 + (size_t)TWN * 2 * sizeof(T) + 16;
+  // contiguous pieces only: lines of a line-major input, block runs of a micro-blocked one
+  if (sg.blocked ? sp.iblk2_stride != (long long)tl * sp.iblk2 : (sp.istride != 1 || sp.iseg_stride != 0)) return cudaErrorInvalidValue;
+  if ((tl * N) % sg.chunk_elems || sg.piece_elems % sg.chunk_elems) return cudaErrorInvalidValue;
+  for (int e = 0; e < E; e++) sp.outp[e] = static_cast<char *>(sp.out[sp.out_seg[e]]) + sp.out_off[e] * (long long)(2 * sizeof(T));
   auto kf = stage_blk_kernel<T, N, E, MAXT, false>;
   auto kb = stage_blk_kernel<T, N, E, MAXT, true>;
   auto kern = sp.sign > 0 ? kb : kf;

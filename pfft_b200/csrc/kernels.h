@@ -50,7 +50,9 @@ struct StageParams {
   const void *tw2, *tw3;     // per-pass twiddle tables [r-1][k]
   // micro-blocked layouts / explicit tiles (core.h: Stage::iblk2 ...): handled by stage_blk_kernel
   int iblk2, oblk2, ntile;
+  int iswz_mask, oswz_mask, oswz_shift, oswz_batch;
   long long iblk2_stride, oblk2_stride;
+  void *outp[16];            // out[out_seg[e]] + out_off[e], resolved at launch
   long long tile_ioff[kMaxTile], tile_ooff[kMaxTile];
   long long in_off[16];      // element offset of line index e*THREADS on input
   long long out_off[16];     // ... on output, inside chunk out_seg[e]

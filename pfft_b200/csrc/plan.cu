@@ -134,6 +134,7 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     sp.iblk2 = (int)g.iblk2; sp.iblk2_stride = g.iblk2_stride;
     sp.oblk2 = (int)g.oblk2; sp.oblk2_stride = g.oblk2_stride;
     sp.ntile = g.ntile;
+    sp.iswz_mask = g.iswz_mask; sp.oswz_mask = g.oswz_mask; sp.oswz_shift = g.oswz_shift; sp.oswz_batch = g.oswz_batch;
     for (int l = 0; l < g.ntile; l++) { sp.tile_ioff[l] = g.tile_ioff[l]; sp.tile_ooff[l] = g.tile_ooff[l]; }
     sp.in_real = g.in_real; sp.out_real = g.out_real; sp.conj_in = g.conj_in; sp.conj_out = g.conj_out;
     sp.mod_in = {g.mod_in.on, (int)g.mod_in.start, (int)g.mod_in.half, g.mod_in.extra};

@@ -42,6 +42,8 @@ struct Layout {
   INT lstride[kMaxDims + 1] = {0};
   int border[kMaxDims + 1] = {0};
   int nbord = 0;
+  int swz_mask = 0;          // lines of a block are XOR-permuted by (block index along seg/gather dim) & swz_mask
+  int swz_dim = -1;          // the gathered dimension (its high part is the block index)
 
   void finish() {
     INT s = 1;
@@ -90,7 +92,7 @@ struct Builder {
   INT cur_ext[kMaxDims + 1];   // current local extents (complex-physical / real as stored)
   // micro-blocked intermediate layouts (plan_microblocks): tile factor of step s along dim t
   bool mbk = false;
-  int mbk_order = 1;           // 1: [others][gather][split] (producer writes contiguously), 2: [others][split][gather]
+  int mbk_order = 2;           // 1: [others][gather][split] (producer writes contiguously), 2: [others][split][gather]
   INT tilef[2 * kMaxDims + 4][kMaxDims + 1];
 
   Builder(const Problem &pp, Schedule &ss) : p(pp), s(ss) {}
@@ -312,6 +314,7 @@ struct Builder {
     if (Lin.mb[a] > 1) {
       g.iblk2 = Lin.mb[a];
       g.iblk2_stride = Lin.stride[a];
+      if (Lin.swz_dim == a) g.iswz_mask = Lin.swz_mask;
     }
     if (Lin.seg_dim == a) {
       g.iblk = Lin.seg_blk;
@@ -359,7 +362,7 @@ struct Builder {
       // the low part (x % f) selects the line inside the tile, the high part enumerates tiles
       if ((mi != 1 && mi != f) || (mo != 1 && mo != f) || Lin.ext[t] % f) { s.error = "internal: tile / micro-block mismatch"; return; }
       td.push_back({f, Lin.lstride[t], Lout.lstride[t]});
-      if (Lin.ext[t] / f > 1)
+      if (Lin.ext[t] / f > 1 || t == Lout.swz_dim)
         b.push_back({Lin.ext[t] / f, mi == f ? Lin.stride[t] : f * Lin.stride[t], mo == f ? Lout.stride[t] : f * Lout.stride[t], t});
     }
     if (!td.empty()) {
@@ -389,6 +392,7 @@ struct Builder {
       for (size_t x = 0; x < b.size() && !merged; x++)
         for (size_t y = 0; y < b.size() && !merged; y++) {
           if (x == y) continue;
+          if (Lout.swz_mask && (b[x].dim == Lout.swz_dim || b[y].dim == Lout.swz_dim)) continue;   // its coordinate drives the swizzle
           if (b[x].istride == b[y].istride * b[y].extent && b[x].ostride == b[y].ostride * b[y].extent) {
             b[y].extent *= b[x].extent;
             b.erase(b.begin() + x);
@@ -419,6 +423,17 @@ struct Builder {
       else g.tile_dim = pick(false);
     }
     if (g.ntile > 0) g.tile_dim = -1;
+    if (g.ntile > 0 && Lout.swz_mask) {
+      // producer side of the swizzle: the block index is the tile's coordinate along the gathered dimension;
+      // the permuted bits are the lowest "other dimension" bits of the line id = just above the gathered low part
+      for (int k = 0; k < g.nbatch; k++)
+        if (g.batch[k].dim == Lout.swz_dim) g.oswz_batch = k;
+      if (g.oswz_batch < 0) { s.error = "internal: swizzle dimension is not a batch dimension"; return; }
+      g.oswz_mask = Lout.swz_mask;
+      INT sh = 0;
+      while (((INT)1 << sh) < Lout.mb[Lout.swz_dim]) sh++;
+      g.oswz_shift = (int)sh;
+    }
     g.in_elems = lines * g.nin;
     g.out_elems = lines * g.nout;
     s.stages.push_back(g);
@@ -478,7 +493,7 @@ struct Builder {
     const char *env = getenv("PFFT_B200_BLOCKED");
     const int mode = env ? atoi(env) : 1;
     if (mode <= 0) return;
-    mbk_order = mode == 2 ? 2 : 1;
+    mbk_order = 2;   // [others][split][gather]: the consuming tile reads one contiguous piece per source rank
     if (p.kind != Kind::C2C || p.howmany != 1 || m3.active || d != r + 1 || d < 2) return;
     if (tr != F_TRANSPOSED_IN && tr != F_TRANSPOSED_OUT) return;
     if ((int)steps.size() != d || p.has_skip || p.has_iblock || p.has_oblock) return;
@@ -733,6 +748,14 @@ struct Builder {
               add(t, Fp[t]);
             }
           add(st.xch_gather, Fp[st.xch_gather]);
+          // bank swizzle: a quarter-warp of the consumer reads 8 / tG consecutive blocks (16-byte words)
+          INT others = 1;
+          for (int t = 0; t <= r; t++)
+            if (t != st.xch_split && t != st.xch_gather) others *= Fp[t];
+          const INT tG = Fp[st.xch_gather];
+          const INT want = tG < 8 ? 8 / tG : 1;
+          Lout.swz_mask = (int)(std::min(want, others) - 1);
+          Lout.swz_dim = st.xch_gather;
         }
         Lout.finish();
         noseg = np[m];
@@ -866,7 +889,8 @@ std::string schedule_to_json(const Schedule &s) {
       << ",\"nout\":" << g.nout << ",\"zout\":" << g.zout << ",\"istride\":" << g.istride
       << ",\"iblk\":" << g.iblk << ",\"iseg_stride\":" << g.iseg_stride << ",\"ostride\":" << g.ostride
       << ",\"oblk\":" << g.oblk << ",\"noseg\":" << g.noseg << ",\"iblk2\":" << g.iblk2 << ",\"iblk2_stride\":" << g.iblk2_stride
-      << ",\"oblk2\":" << g.oblk2 << ",\"oblk2_stride\":" << g.oblk2_stride << ",\"ntile\":" << g.ntile << ",\"tile_ioff\":";
+      << ",\"oblk2\":" << g.oblk2 << ",\"oblk2_stride\":" << g.oblk2_stride << ",\"ntile\":" << g.ntile << ",\"iswz_mask\":" << g.iswz_mask << ",\"oswz_mask\":" << g.oswz_mask
+      << ",\"oswz_shift\":" << g.oswz_shift << ",\"oswz_batch\":" << g.oswz_batch << ",\"tile_ioff\":";
     arr(g.tile_ioff, g.ntile);
     o << ",\"tile_ooff\":";
     arr(g.tile_ooff, g.ntile);

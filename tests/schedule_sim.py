@@ -65,21 +65,35 @@ def run_stage(g, inbuf):
     nb = len(g["batch"])
     lin = np.zeros((), dtype=np.int64)
     lout = np.zeros((), dtype=np.int64)
+    swz_c = np.zeros((), dtype=np.int64)     # batch coordinate that drives the producer-side swizzle
     for k, (ext, is_, os_, _dim) in enumerate(g["batch"]):
         idx = np.arange(ext, dtype=np.int64)
         shape = [1] * nb
         shape[k] = ext
         lin = lin + (idx * is_).reshape(shape)
         lout = lout + (idx * os_).reshape(shape)
+        if k == g.get("oswz_batch", -1):
+            swz_c = swz_c + idx.reshape(shape)
+    swz_c = np.broadcast_to(swz_c, np.broadcast(lin, lout, swz_c).shape).reshape(-1) if nb else np.zeros(1, dtype=np.int64)
     lin = np.asarray(lin).reshape(-1)
     lout = np.asarray(lout).reshape(-1)
     if any(b[0] == 0 for b in g["batch"]):
         lin = lin[:0]
         lout = lout[:0]
+    line_id = None
     if g.get("ntile", 0) > 0:
         # explicit tiles (micro-blocked layouts): batch[] enumerates tiles, the tables place the lines of a tile
-        lin = (lin[:, None] + np.asarray(g["tile_ioff"], dtype=np.int64)[None, :]).reshape(-1)
-        lout = (lout[:, None] + np.asarray(g["tile_ooff"], dtype=np.int64)[None, :]).reshape(-1)
+        nt = g["ntile"]
+        tio = np.asarray(g["tile_ioff"], dtype=np.int64)
+        too = np.asarray(g["tile_ooff"], dtype=np.int64)
+        l = np.arange(nt, dtype=np.int64)
+        m = (swz_c & g.get("oswz_mask", 0)) << g.get("oswz_shift", 0)
+        lout = (lout[:, None] + (too[None, :] ^ m[:, None])).reshape(-1)
+        if g.get("iswz_mask", 0):
+            line_id = np.tile(l, lin.size)           # the input offset of a line depends on the block index
+            lin = np.repeat(lin, nt)
+        else:
+            lin = (lin[:, None] + tio[None, :]).reshape(-1)
     out_dtype = np.float64 if g["out_real"] else np.complex128
     chunks = [np.zeros(c, dtype=out_dtype) for c in g["oseg_cnt"]]
     nin, n, nout = g["nin"], g["n"], g["nout"]
@@ -90,7 +104,12 @@ def run_stage(g, inbuf):
     jl = j - seg * g["iblk"]
     b2 = g.get("iblk2", 1)
     in_idx = seg * g["iseg_stride"] + (jl * g["istride"] if b2 == 1 else (jl // b2) * g["iblk2_stride"] + (jl % b2) * g["istride"])
-    X = inbuf[lin[:, None] + in_idx[None, :]]
+    if line_id is None:
+        X = inbuf[lin[:, None] + in_idx[None, :]]
+    else:
+        blk = ((jl // b2) & g["iswz_mask"]) * b2     # XOR on the in-block offset, just above the line-index part
+        tio = np.asarray(g["tile_ioff"], dtype=np.int64)
+        X = inbuf[lin[:, None] + (tio[line_id][:, None] ^ blk[None, :]) + in_idx[None, :]]
     if g["conj_in"]:
         X = np.conj(X)
     f = _sign_mod(g["mod_in"], nin)
