@@ -307,3 +307,46 @@ def test_ghost_cells_match_oracle(built_lib, case):
         sl = tuple(slice(r["local_start"][t], r["local_start"][t] + r["local_n"][t]) for t in range(3))
         assert np.allclose(red, summed[sl], rtol=1e-14, atol=1e-14)
         assert np.all(r["out"][tot + cnt:2 * tot] == 0), "tail must be zeroed after reduce"
+
+
+# ---- BASELINE.json configs 3-5 at their full sizes (8 ranks; they share the GPU on a 1-GPU box)
+PAD_C2R = po.PADDED_R2C   # PFFT_PADDED_C2R is the same bit (reference api/pfft.h:540-541)
+BASELINE_CONFIGS = [
+    dict(tag="config3-r2c-fp32-1024-padded-inplace", kind="r2c", n=[1024, 1024, 1024], np=[2, 4], precision="single",
+         flags_forward=T_OUT | PAD, flags_backward=T_IN | PAD_C2R, inplace=True, tol=1500 * 2e-5),
+    dict(tag="config4-c2c-128^4-on-2x2x2", kind="c2c", n=[128, 128, 128, 128], np=[2, 2, 2],
+         flags_forward=T_OUT, flags_backward=T_IN, tol=1e-12),
+    dict(tag="config5-ousam-r2c-512-to-768-gcell", kind="r2c", n=[768, 768, 768], ni=[512, 512, 512], np=[2, 4],
+         flags_forward=T_OUT, flags_backward=T_IN, gc=dict(below=[2, 2, 0], above=[3, 3, 0]), tol=1e-12),
+]
+
+
+@pytest.mark.parametrize("cfg", BASELINE_CONFIGS, ids=lambda c: c["tag"])
+def test_baseline_configs_round_trip_at_full_size(built_lib, cfg):
+    P = int(np.prod(cfg["np"]))
+    with tempfile.TemporaryDirectory() as td:
+        json.dump(cfg, open(os.path.join(td, "cfg.json"), "w"))
+        cmd = [os.path.join(ROOT, "pfft_b200", "bin", "pfftrun"), "-np", str(P), "-timeout", "500",
+               sys.executable, os.path.join(ROOT, "tests", "baseline_worker.py"), os.path.join(td, "cfg.json"), td]
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=560)
+        assert p.returncode == 0, (p.returncode, p.stdout[-2000:], p.stderr[-2000:])
+        res = [json.load(open(os.path.join(td, "rank%d.json" % rk))) for rk in range(P)]
+    for r in res:
+        assert r["error"] == "", r["error"]
+    # the reference's acceptance rule: pfft_check_output_* (a maximum over all ranks)
+    assert max(r["maxerror"] for r in res) < cfg["tol"], [r["maxerror"] for r in res]
+    # decomposition of the last rank as captured from the reference's own code
+    if cfg["tag"].startswith("config3"):
+        assert (res[7]["local_ni"], res[7]["local_i_start"], res[7]["local_no"]) == ([512, 256, 1026], [512, 768, 0], [1024, 512, 126])
+    if cfg["tag"].startswith("config4"):
+        assert (res[7]["local_ni"], res[7]["local_no"]) == ([64, 64, 64, 128], [128, 64, 64, 64])
+    if cfg.get("gc"):
+        assert (res[7]["local_ni"], res[7]["local_no"]) == ([256, 128, 512], [768, 384, 94])
+        g7 = res[7]["gc"]
+        assert (g7["ngc"], g7["gc_start"], g7["mem"]) == ([261, 133, 512], [254, 382, 0], 17773056)
+        for r in res:
+            g = r["gc"]
+            assert g["error"] == "" and g["exchange_maxerr"] == 0.0 and g["tail_zero"]
+        # reduce is the adjoint of exchange: what all ghost-cell blocks held is what the owners hold afterwards
+        ex, red = sum(r["gc"]["exchanged_sum"] for r in res), sum(r["gc"]["reduced_sum"] for r in res)
+        assert abs(ex - red) <= 1e-12 * abs(ex), (ex, red)
