@@ -58,6 +58,14 @@ void *fftwf_malloc(size_t n);
 float *fftwf_alloc_real(size_t n);
 fftwf_complex *fftwf_alloc_complex(size_t n);
 void fftwf_free(void *p);
+
+/* The few FFTW planner/executor names PFFT programs use to compare PFFT with FFTW
+ * (/root/reference/tests/bench_c2c.c:272-398, `-pfft_cmp_fftw`).  NOT FFTW: the same sm_100a stage
+ * kernels behind a one-rank (fftw_plan_dft_3d) or 1-D slab (fftw_mpi_plan_dft_3d, fftw3-mpi.h) mesh. */
+typedef struct pfft_b200_fftw_plan_s *fftw_plan;
+fftw_plan fftw_plan_dft_3d(int n0, int n1, int n2, fftw_complex *in, fftw_complex *out, int sign, unsigned flags);
+void fftw_execute(const fftw_plan p);
+void fftw_destroy_plan(fftw_plan p);
 #ifdef __cplusplus
 }
 #endif

@@ -568,6 +568,73 @@ void *fftwf_alloc_complex(size_t n) { return managed_alloc(n * 2 * sizeof(float)
 void fftwf_free(void *p) { if (p) { cudaDeviceSynchronize(); cudaFree(p); } }
 }
 
+// ---- the slab interface of FFTW-MPI that PFFT programs use for comparisons ---------------------
+// (reference tests/bench_c2c.c:272-398 `-pfft_cmp_fftw`).  Not FFTW: the same stage kernels behind a
+// 1-D process mesh -- FFTW-MPI's slab decomposition [n0/P][n1][n2] and its transposed output
+// [n1/P][n0][n2] are exactly PFFT's layouts on a 1-D mesh (reference doc/intro.tex, api/pfft.h:423).
+namespace {
+struct FftwCompatPlan {
+  pfft_plan_s *plan;
+  MPI_Comm cart;
+};
+unsigned fftw_flags_to_pfft(unsigned f) {
+  unsigned fl = 0;
+  if (f & (1u << 29)) fl |= F_TRANSPOSED_IN;    // FFTW_MPI_TRANSPOSED_IN
+  if (f & (1u << 30)) fl |= F_TRANSPOSED_OUT;   // FFTW_MPI_TRANSPOSED_OUT
+  if (f & (1u << 0)) fl |= F_DESTROY_INPUT;     // FFTW_DESTROY_INPUT
+  return fl;
+}
+}  // namespace
+
+extern "C" {
+ptrdiff_t fftw_mpi_local_size_3d_transposed(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, MPI_Comm comm, ptrdiff_t *local_n0,
+                                            ptrdiff_t *local_0_start, ptrdiff_t *local_n1, ptrdiff_t *local_1_start) {
+  const INT n[3] = {n0, n1, n2};
+  INT lni[3], lis[3], lno[3], los[3];
+  MPI_Comm cart = MPI_COMM_NULL;
+  int np = 1;
+  MPI_Comm_size(comm, &np);
+  if (pfft_create_procmesh_1d(comm, np, &cart)) return 0;
+  const INT alloc = pfft_local_size_dft_3d(n, cart, F_TRANSPOSED_OUT, lni, lis, lno, los);
+  MPI_Comm_free(&cart);
+  *local_n0 = lni[0];
+  *local_0_start = lis[0];
+  *local_n1 = lno[1];       // PFFT reports the transposed block in logical order: dimension 1 is the split one
+  *local_1_start = los[1];
+  return alloc;
+}
+
+void *fftw_mpi_plan_dft_3d(ptrdiff_t n0, ptrdiff_t n1, ptrdiff_t n2, void *in, void *out, MPI_Comm comm, int sign, unsigned flags) {
+  const INT n[3] = {n0, n1, n2};
+  MPI_Comm cart = MPI_COMM_NULL;
+  int np = 1;
+  MPI_Comm_size(comm, &np);
+  if (pfft_create_procmesh_1d(comm, np, &cart)) return nullptr;
+  pfft_plan_s *pl = pfft_plan_dft_3d(n, in, out, cart, sign, fftw_flags_to_pfft(flags));
+  if (!pl) {
+    MPI_Comm_free(&cart);
+    return nullptr;
+  }
+  return new FftwCompatPlan{pl, cart};
+}
+
+void *fftw_plan_dft_3d(int n0, int n1, int n2, void *in, void *out, int sign, unsigned flags) {
+  return fftw_mpi_plan_dft_3d(n0, n1, n2, in, out, MPI_COMM_SELF, sign, flags);
+}
+
+void fftw_execute(void *p) {
+  if (p) pfft_execute(static_cast<FftwCompatPlan *>(p)->plan);
+}
+
+void fftw_destroy_plan(void *p) {
+  if (!p) return;
+  FftwCompatPlan *c = static_cast<FftwCompatPlan *>(p);
+  pfft_destroy_plan(c->plan);
+  MPI_Comm_free(&c->cart);
+  delete c;
+}
+}
+
 // ---- extensions -------------------------------------------------------------------------
 namespace pfb { void set_default_transport(int t); }
 

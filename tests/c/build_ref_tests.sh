@@ -42,4 +42,12 @@ for name in $LIST2D $LIST3D; do
     echo "SKIPPED (does not compile): $name" >> "$OUT/BUILD_LOG"
   fi
 done
-echo "built $(cat "$OUT/LIST_2D" "$OUT/LIST_3D" | wc -l) reference test programs into $OUT"
+# the reference's benchmark program (tests/bench_c2c.c): command-line driven, run by its own test
+: > "$OUT/LIST_BENCH"
+if gcc -std=gnu99 -O1 -w -I"$ROOT/include" "$REF/tests/bench_c2c.c" -o "$OUT/bench_c2c" \
+     -L"$ROOT/pfft_b200/lib" -lpfft_b200 -lm -Wl,-rpath,'$ORIGIN/../../../pfft_b200/lib' >>"$OUT/BUILD_LOG" 2>&1; then
+  echo "bench_c2c" >> "$OUT/LIST_BENCH"
+else
+  echo "SKIPPED (does not compile): bench_c2c" >> "$OUT/BUILD_LOG"
+fi
+echo "built $(cat "$OUT/LIST_2D" "$OUT/LIST_3D" "$OUT/LIST_BENCH" | wc -l) reference test programs into $OUT"

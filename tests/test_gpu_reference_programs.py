@@ -39,6 +39,34 @@ def test_reference_program(built_lib, name, np_):
     assert max(errs) < tol, (errs, p.stdout[-800:])
 
 
+BENCH_RUNS = [
+    # (ranks, arguments): pencil mesh transposed, 3-D mesh, slab with the FFTW-MPI-style comparison path,
+    # one rank with the serial comparison path, in place
+    (4, "-pfft_n 64 64 64 -pfft_np 2 2 1 -pfft_loops 1 -pfft_transposed -pfft_timer"),
+    (8, "-pfft_n 32 48 64 -pfft_np 2 2 2 -pfft_loops 1"),
+    (2, "-pfft_n 64 32 16 -pfft_np 2 1 1 -pfft_loops 1 -pfft_transposed -pfft_cmp_fftw"),
+    (1, "-pfft_n 32 32 32 -pfft_np 1 1 1 -pfft_loops 1 -pfft_cmp_fftw"),
+    (4, "-pfft_n 128 128 128 -pfft_np 2 2 1 -pfft_loops 1 -pfft_transposed -pfft_inplace -pfft_destroy_input"),
+]
+
+
+@pytest.mark.parametrize("np_,args", BENCH_RUNS, ids=[a.replace("-pfft_", "").replace(" ", "_") for _, a in BENCH_RUNS])
+def test_reference_benchmark_program(built_lib, np_, args):
+    """tests/bench_c2c.c of the reference, unmodified, as the harness: every `error =` line
+    it prints (pfft_check_output after forward + backward) must meet the reference's 1e-12."""
+    exe = os.path.join(BIN, "bench_c2c")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bin/bench_c2c missing (built only where /root/reference exists)")
+    cmd = [os.path.join(ROOT, "pfft_b200", "bin", "pfftrun"), "-np", str(np_), "-timeout", "120", exe] + args.split()
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+    assert p.returncode == 0, (p.returncode, p.stdout[-1500:], p.stderr[-1500:])
+    errs = [float(x) for x in re.findall(r"error = ([-+0-9.eE]+)", p.stdout)]
+    assert errs and "exec_forw/loops" in p.stdout, p.stdout[-1500:]
+    if "-pfft_cmp_fftw" in args:
+        assert "FFTW" in p.stdout and len(errs) >= 2, p.stdout[-1500:]
+    assert max(errs) < 1e-12, (errs, p.stdout[-800:])
+
+
 def test_programs_were_built():
     if not os.path.isdir(BIN):
         pytest.skip("oracle/_ref/bin missing (built only where /root/reference exists)")
