@@ -86,7 +86,7 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(0.05)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._run, daemon=True)

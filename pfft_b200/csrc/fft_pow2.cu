@@ -853,25 +853,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 
-// butterflies of one pass, outputs left in registers: output q of butterfly b in x[b + q * B].
-// W3MUL (radix 4 only): the table holds w^k and w^2k; w^3k is their product.
-template <typename T, int N, int E, int R, int NS, bool W3MUL>
+// butterflies of one pass, outputs left in registers: output q of butterfly b in x[b + q * B]
+template <typename T, int N, int E, int R, int NS>
 __device__ __forceinline__ void pass_regs(cx<T> *x, int t, const cx<T> *__restrict__ twp) {
-  if constexpr (!W3MUL) {
-    pass<T, N, E, R, NS, true>(x, t, twp, nullptr);
-  } else {
-    static_assert(R == 4, "w^3 = w * w^2 is for the radix-4 pass");
-    constexpr int THREADS = N / E;
-    constexpr int B = E / R;
-#pragma unroll
-    for (int b = 0; b < B; b++) {
-      const int k = (t + b * THREADS) & (NS - 1);
-      const cx<T> w1 = twp[k], w2 = twp[NS + k];
-      cx<T> v[4] = {x[b], cmul(x[b + B], w1), cmul(x[b + 2 * B], w2), cmul(x[b + 3 * B], cmul(w1, w2))};
-      dft4(v[0], v[1], v[2], v[3]);
-      x[b] = v[0]; x[b + B] = v[1]; x[b + 2 * B] = v[2]; x[b + 3 * B] = v[3];
-    }
-  }
+  pass<T, N, E, R, NS, true>(x, t, twp, nullptr);
 }
 // where pass (R, NS) puts output q of butterfly b: index into a padded line of 8-byte words
 template <int N, int E, int R, int NS>
@@ -935,7 +920,6 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
   constexpr bool SPLIT = sizeof(T) == 8;                 // exchange real and imaginary parts separately
   using XE = typename std::conditional<SPLIT, T, cx<T>>::type;   // 8-byte exchange word
   static_assert(sizeof(XE) == 8, "exchange words are 8 bytes");
-  constexpr bool W3MUL = false;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tl = sp.tl;
   const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, (int)sizeof(cx<T>));
@@ -1044,7 +1028,7 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
       x[e].y = BWD ? r.x : r.y;
     }
     mbar_arrive(bar_empty);          // my part of the staging buffer may be overwritten
-    pass_regs<T, N, E, P::R1, 1, false>(x, t_c, nullptr);
+    pass_regs<T, N, E, P::R1, 1>(x, t_c, nullptr);
     const long long obase_cur = obase;
     const unsigned next = tile + gridDim.x;
     if (next < ntiles) locate(next, ibase, obase);
@@ -1072,7 +1056,7 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
     if (P::NPASS == 3) {
       PFB_EXCHANGE(P::R1, 1, my_x, t_c, pt_c, per_line)
       sync_lines(per_line);          // the line's words are free again
-      pass_regs<T, N, E, P::R2, P::R1, false>(x, t_c, tw2);
+      pass_regs<T, N, E, P::R2, P::R1>(x, t_c, tw2);
     }
     // fetch the next tile (its staging buffer must have been emptied by everybody; that was long ago)
     if (next < ntiles) {
@@ -1082,11 +1066,11 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
     if (P::NPASS == 3) {
       PFB_EXCHANGE(P::R2, P::R1, out_x, t_s, pt_s, lbar_out)
       if (lbar_out) sync_lines(true);
-      pass_regs<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2, W3MUL>(x, t_s, tw3);
+      pass_regs<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2>(x, t_s, tw3);
     } else {
       PFB_EXCHANGE(P::R1, 1, out_x, t_s, pt_s, lbar_out)
       if (lbar_out) sync_lines(true);
-      pass_regs<T, N, E, P::R2, P::R1, false>(x, t_s, tw2);
+      pass_regs<T, N, E, P::R2, P::R1>(x, t_s, tw2);
     }
 #undef PFB_EXCHANGE
     const long long thread_off = obase_cur + out_point;

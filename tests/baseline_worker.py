@@ -58,6 +58,8 @@ def round_trip(cfg, comm):
     if b is not a:      # (in place the array holds the forward result)
         pf.clear_input(pattern, ni, lni, lis, a, dtype=real)
     bwd.execute()
+    out["stage_ms_forward"], out["stage_ms_backward"] = fwd.stage_times_ms(), bwd.stage_times_ms()
+    out["kernels_backward"] = bwd.describe()["kernels"]
     cnt = int(np.prod(lni))
     a.array[:cnt] /= float(np.prod(n))
     out["maxerror"] = pf.check_output(pattern, ni, lni, lis, a, comm, dtype=real)

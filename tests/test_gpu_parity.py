@@ -333,6 +333,9 @@ def test_baseline_configs_round_trip_at_full_size(built_lib, cfg):
         res = [json.load(open(os.path.join(td, "rank%d.json" % rk))) for rk in range(P)]
     for r in res:
         assert r["error"] == "", r["error"]
+    print("\n%s: kernels %s / %s, stage ms (rank 0, ranks share the GPU) forward %s backward %s" % (
+        cfg["tag"], res[0]["kernels_forward"], res[0]["kernels_backward"],
+        [round(v, 2) for v in res[0]["stage_ms_forward"]], [round(v, 2) for v in res[0]["stage_ms_backward"]]))
     # the reference's acceptance rule: pfft_check_output_* (a maximum over all ranks)
     assert max(r["maxerror"] for r in res) < cfg["tol"], [r["maxerror"] for r in res]
     # decomposition of the last rank as captured from the reference's own code
