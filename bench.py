@@ -260,7 +260,7 @@ def main():
                 "t_roof_serial_ms": t_hbm + t_nvl, "t_roof_overlap_ms": max(t_hbm, t_nvl),
                 "t_measured_ms": t_transform, "frac_of_serial_roofline": (t_hbm + t_nvl) / t_transform,
                 "nvlink_gbs_in_exchange_stages": None}
-    if world > 1:
+    if world > 1 and desc["transport"] == "p2p":
         # stages in front of a real exchange push their remote chunks over NVLink inside the kernel
         rates = []
         fm = roofline_stage = [sum(r[i] for r in stage_ms_f) / len(stage_ms_f) for i in range(len(stage_ms_f[0]))]

@@ -63,6 +63,20 @@ def round_trip(cfg, comm):
     cnt = int(np.prod(lni))
     a.array[:cnt] /= float(np.prod(n))
     out["maxerror"] = pf.check_output(pattern, ni, lni, lis, a, comm, dtype=real)
+    if cfg.get("time_pairs"):
+        # timing (profiles/time_baseline_configs.py): one untimed pair brings the managed arrays back to the
+        # GPU, then `time_pairs` forward+backward pairs, wall clock between barriers, max over ranks
+        import time
+        fwd.execute()
+        bwd.execute()
+        comm.barrier()
+        t0 = time.perf_counter()
+        for _ in range(cfg["time_pairs"]):
+            fwd.execute()
+            bwd.execute()
+        comm.barrier()
+        out["ms_per_pair"] = comm.allreduce_max((time.perf_counter() - t0) / cfg["time_pairs"] * 1e3)
+        out["stage_ms_forward"], out["stage_ms_backward"] = fwd.stage_times_ms(), bwd.stage_times_ms()
     fwd.destroy()
     bwd.destroy()
     a.free()
