@@ -241,8 +241,10 @@ __device__ __forceinline__ void cp_async_zfill(unsigned dst_smem, const void *sr
   const int n = ok ? BYTES : 0;
   if (BYTES == 16)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
-  else
+  else if (BYTES == 8)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
 }
 
 template <int BYTES>
@@ -287,6 +289,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   const int t_out = out_line_major ? tid % THREADS : tid / tl;
   const int tt_out = out_line_major ? tid / THREADS : tid % tl;
   const bool backward = DIR == 0 ? sp.sign > 0 : DIR == 2;
+  const bool c2r_line = !FAST && sp.op == OP_C2R;   // Hermitian half spectrum in, real line out
   // Barriers between passes: while a line is handled by whole warps of its own (line-major
   // mapping), only those warps need to meet -- named barrier 1 + line -- so the lines of a tile
   // drift apart and their load / butterfly / exchange phases overlap.  Where the store mapping is
@@ -344,11 +347,13 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
           cp_async_plain<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)), in + sp.in_off[e]);
       }
     } else {
-      const cx<T> *in = reinterpret_cast<const cx<T> *>(sp.in) + ibase + (long long)tt_in * t_is;
+      const long long line0 = ibase + (long long)tt_in * t_is;
       const bool seg_in = sp.iseg_stride != 0;
 #pragma unroll
       for (int e = 0; e < E; e++) {
-        const int j = t_in + e * THREADS - sp.zin;   // position in the input line
+        int j = t_in + e * THREADS - sp.zin;   // position in the input line
+        // c2r: the upper half of the spectrum is the mirrored, conjugated lower half (conjugation on pick-up)
+        if (c2r_line && j > N / 2) j = N - j;
         const bool ok = live && j >= 0 && j < sp.nin;
         long long off = 0;
         if (ok) {
@@ -359,8 +364,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
             off = (long long)j * sp.istride;
           }
         }
-        cp_async_zfill<sizeof(cx<T>)>(my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>)),
-                                      ok ? (const void *)(in + off) : sp.in, ok);
+        const unsigned dst = my_line_in_s + (unsigned)(phys(t_in + e * THREADS) * sizeof(cx<T>));
+        if (sp.in_real)      // r2c: real parts only (strides count reals); the imaginary half of the slot is ignored
+          cp_async_zfill<sizeof(T)>(dst, ok ? (const void *)(reinterpret_cast<const T *>(sp.in) + line0 + off) : sp.in, ok);
+        else
+          cp_async_zfill<sizeof(cx<T>)>(dst, ok ? (const void *)(reinterpret_cast<const cx<T> *>(sp.in) + line0 + off) : sp.in, ok);
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -383,6 +391,8 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
       for (int e = 0; e < E; e++) {
         const cx<T> r = my_line_in[phys(t_in + e * THREADS)];
         T re = r.x, im = cj ? -r.y : r.y;
+        if (!FAST && sp.in_real) im = 0;
+        if (c2r_line && t_in + e * THREADS - sp.zin > N / 2) im = -im;
         if (!FAST && sp.mod_in.on) {
           if (sign_mod_dev(sp.mod_in, t_in + e * THREADS - sp.zin) < 0) { re = -re; im = -im; }
         }
@@ -453,8 +463,9 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
             seg = kk / sp.oblk;
             kl = kk - seg * sp.oblk;
           }
-          cx<T> *out = reinterpret_cast<cx<T> *>(sp.out[seg]) + obase_cur + (long long)tt_out * t_os + (long long)kl * sp.ostride;
-          *reinterpret_cast<V *>(out) = raw;
+          const long long off = obase_cur + (long long)tt_out * t_os + (long long)kl * sp.ostride;
+          if (sp.out_real) reinterpret_cast<T *>(sp.out[seg])[off] = raw.x;      // c2r: strides count reals
+          else *reinterpret_cast<V *>(reinterpret_cast<cx<T> *>(sp.out[seg]) + off) = raw;
         }
       }
     }
@@ -1191,9 +1202,16 @@ int points_per_thread(int n) { return pow2_points_per_thread(n); }   // core.h: 
 
 template <typename T>
 bool pow2_supported(const Stage &g, int L) {
-  if (g.op != OP_C2C) return false;
   if (L < 64 || L > 4096 || (L & (L - 1))) return false;
-  if (g.in_real || g.out_real) return false;
+  // real lines run as a full-length complex transform: r2c with imaginary parts zero (the kept outputs are
+  // the first n/2+1), c2r with the upper half of the spectrum completed by Hermitian symmetry on load
+  if (g.op == OP_R2C) {
+    if (!g.in_real || g.out_real) return false;
+  } else if (g.op == OP_C2R) {
+    if (g.in_real || !g.out_real || g.zin != 0 || g.nin != L / 2 + 1) return false;
+  } else if (g.op != OP_C2C || g.in_real || g.out_real) {
+    return false;
+  }
   if (g.noseg > kMaxSeg) return false;
   long long lines = 1;
   for (int k = 0; k < g.nbatch; k++) {
@@ -1302,7 +1320,7 @@ void pow2_prepare(const Stage &g, StageParams &sp) {
   const int L = sp.L;
   const int E = points_per_thread(L);
   const int threads = L / E;
-  bool fast = g.nin == L && g.zin == 0 && g.nout == L && g.zout == 0 && !g.mod_in.on && !g.mod_out.on && !g.conj_in && !g.conj_out;
+  bool fast = g.op == OP_C2C && g.nin == L && g.zin == 0 && g.nout == L && g.zout == 0 && !g.mod_in.on && !g.mod_out.on && !g.conj_in && !g.conj_out;
   const bool seg_in = g.iseg_stride != 0 && g.iblk < g.nin;
   const bool seg_out = g.noseg > 1;
   if (seg_in && g.iblk % threads != 0) fast = false;

@@ -25,7 +25,10 @@ CONFIGS = [
 
 def main():
     single = len(sys.argv) > 1 and sys.argv[1] == "1"      # one rank on a 1x1 mesh: kernel throughput without exchanges
+    only = sys.argv[2] if len(sys.argv) > 2 else ""          # substring filter on the tag
     for cfg in CONFIGS:
+        if only not in cfg["tag"]:
+            continue
         cfg = dict(cfg, time_pairs=5)
         if single:
             cfg["np"] = [1] * len(cfg["np"])

@@ -66,6 +66,14 @@ SINGLE_RANK = [
     dict(kind="c2r", n=[32, 16, 64], np=[1, 1], flags=T_IN | PAD, sign=+1),
     dict(kind="c2r", n=[16, 12, 10], np=[1, 1], sign=-1),
     dict(kind="r2c", n=[32, 16, 64], np=[1, 1], precision="single", flags=T_OUT | PAD),
+    # real lines of power-of-two length through the register-resident kernel (full-length complex transform)
+    dict(kind="r2c", n=[8, 16, 256], np=[1, 1]),
+    dict(kind="c2r", n=[8, 16, 256], np=[1, 1], sign=+1),
+    dict(kind="r2c", n=[16, 8, 1024], np=[1, 1], flags=T_OUT | PAD, precision="single"),
+    dict(kind="c2r", n=[16, 8, 1024], np=[1, 1], flags=T_IN | PAD, sign=+1, precision="single"),
+    dict(kind="c2r", n=[8, 16, 128], np=[1, 1], flags=T_IN, sign=-1),
+    dict(kind="r2c", n=[8, 16, 128], np=[1, 1], flags=T_OUT, sign=+1),
+    dict(kind="r2c", n=[12, 10, 128], ni=[6, 5, 64], no=[12, 10, 128], np=[1, 1], flags=T_OUT),
     dict(kind="c2c", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[1, 1]),
     dict(kind="c2c", n=[12, 10, 9], ni=[12, 10, 9], no=[5, 7, 3], np=[1, 1], flags=T_OUT),
     dict(kind="r2c", n=[29, 27, 31], ni=[16, 16, 16], no=[29, 27, 31], np=[1, 1], flags=T_OUT),
@@ -128,6 +136,8 @@ MULTI_RANK = [
     dict(kind="c2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_IN, sign=+1),
     dict(kind="r2c", n=[29, 27, 31], np=[2, 2, 2], flags=T_OUT),
     dict(kind="c2c", n=[64, 64, 64], np=[1, 2, 4], flags=T_OUT),
+    dict(kind="r2c", n=[64, 64, 128], np=[2, 2], flags=T_OUT, tag="-pow2real"),
+    dict(kind="c2r", n=[64, 64, 128], np=[2, 2], flags=T_IN, sign=+1, tag="-pow2real"),
     # micro-blocked chains of power-of-two stages across exchanges
     dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_OUT, tag="-blk"),
     dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_IN, sign=+1, tag="-blk"),
