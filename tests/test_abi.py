@@ -22,7 +22,8 @@ def declared_symbols():
         for prefix in ("pfft_", "pfftf_"):
             names.add(prefix + m.group(1))
     for hdr, pat in (("mpi.h", r"\b(MPI_\w+|minimpi_\w+)\s*\("), ("pfft_b200.h", r"\b(pfftb200_\w+)\s*\("),
-                     ("fftw3.h", r"\b(fftwf?_(?:malloc|alloc_real|alloc_complex|free))\s*\(")):
+                     ("fftw3.h", r"\b(fftwf?_(?:malloc|alloc_real|alloc_complex|free|plan_dft_3d|execute|destroy_plan))\s*\("),
+                     ("fftw3-mpi.h", r"\b(fftw_mpi_\w+)\s*\(")):
         text = open(os.path.join(INC, hdr)).read()
         text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
         text = "\n".join(l for l in text.splitlines() if not l.lstrip().startswith("#"))   # macros are not symbols
