@@ -9,10 +9,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import pfft_oracle as po  # noqa: E402
-
-T_IN, T_OUT, PAD = po.TRANSPOSED_IN, po.TRANSPOSED_OUT, po.PADDED_R2C
+T_IN, T_OUT, PAD = 1 << 0, 1 << 1, 1 << 11      # PFFT_TRANSPOSED_IN / _OUT, PFFT_PADDED_R2C (include/pfft.h)
 CONFIGS = [
     dict(tag="config2 c2c fp64 512^3 2x4", kind="c2c", n=[512] * 3, np=[2, 4], flags_forward=T_OUT, flags_backward=T_IN),
     dict(tag="config3 r2c/c2r fp32 1024^3 padded in place 2x4", kind="r2c", n=[1024] * 3, np=[2, 4], precision="single",
