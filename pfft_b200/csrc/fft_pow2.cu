@@ -936,7 +936,11 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
   const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, (int)sizeof(cx<T>));
   // exchange buffer: lines of a tile must fall into different banks for the tile-minor gathers
   // (8 lines x 2 x 8-byte words per half-warp: pitch = 2 mod 16)
-  const int pitch_x = N + (N >> 4) + 2;
+  // Half-CTA mode (stages whose chunks are all local): the change to the tile-minor store mapping is
+  // done inside groups of tl/2 lines with 256-thread named barriers, so the two halves of the CTA drift
+  // apart like the lines do; a warp then stores tl/2 lines x 8 points = 64-byte pieces, merged in L2.
+  const bool grouped = sp.half_cta != 0;
+  const int pitch_x = N + (N >> 4) + (grouped ? 4 : 2);
   cx<T> *stage = reinterpret_cast<cx<T> *>(smem_raw);
   XE *xbuf = reinterpret_cast<XE *>(stage + (size_t)tl * N);
   constexpr int TW2 = (P::R2 - 1) * P::R1;
@@ -961,11 +965,14 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
 
   const bool out_lm = sp.oblk2 == 1;                             // line-major mapping on the output side
   const int t_c = tid % THREADS, tt_c = tid / THREADS;           // butterflies
-  const int t_s = out_lm ? t_c : tid / tl, tt_s = out_lm ? tt_c : tid % tl;
+  const int lg = tl >> 1, grp = tid >> 8, u = tid & 255;         // half-CTA mode: lines per group, my group
+  const int t_s = out_lm ? t_c : (grouped ? u / lg : tid / tl);
+  const int tt_s = out_lm ? tt_c : (grouped ? grp * lg + u % lg : tid % tl);
   const bool per_line = (THREADS % 32 == 0) && tl <= 15;
   const bool lbar_out = per_line && out_lm;
   auto sync_lines = [&](bool pl) {
     if (pl) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_c), "n"(THREADS) : "memory");
+    else if (grouped) asm volatile("bar.sync %0, 256;" ::"r"(9 + grp) : "memory");
     else __syncthreads();
   };
   // my E input points inside the staging buffer: first + e * step
@@ -1045,7 +1052,7 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
     if (next < ntiles) locate(next, ibase, obase);
     // tile-minor output: the previous tile's last gather read every line of xbuf; everybody is past it once
     // everybody has emptied the staging buffer of this tile
-    if (!lbar_out) mbar_wait(bar_empty, phase);
+    if (!lbar_out && !grouped) mbar_wait(bar_empty, phase);
 #define PFB_EXCHANGE(R_, NS_, SRC, T_, PT_, PL)                                             \
   if constexpr (SPLIT) {                                                                    \
     T re_[E];                                                                               \
@@ -1071,16 +1078,18 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
     }
     // fetch the next tile (its staging buffer must have been emptied by everybody; that was long ago)
     if (next < ntiles) {
-      if (lbar_out && (loader || tid == 0)) mbar_wait(bar_empty, phase);
+      if ((lbar_out || grouped) && (loader || tid == 0)) mbar_wait(bar_empty, phase);
       prefetch(ibase);
     }
     if (P::NPASS == 3) {
       PFB_EXCHANGE(P::R2, P::R1, out_x, t_s, pt_s, lbar_out)
       if (lbar_out) sync_lines(true);
+      else if (grouped) sync_lines(false);     // my group's words are free for the next tile
       pass_regs<T, N, E, (P::R3 > 1 ? P::R3 : 2), P::R1 * P::R2>(x, t_s, tw3);
     } else {
       PFB_EXCHANGE(P::R1, 1, out_x, t_s, pt_s, lbar_out)
       if (lbar_out) sync_lines(true);
+      else if (grouped) sync_lines(false);
       pass_regs<T, N, E, P::R2, P::R1>(x, t_s, tw2);
     }
 #undef PFB_EXCHANGE
@@ -1102,7 +1111,14 @@ cudaError_t launch_blk_class(StageParams &sp, cudaStream_t stream) {
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const int tl = sp.tl;
   const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, 2 * (int)sizeof(T));
-  const size_t pitch_x = N + (N >> 4) + 2;
+  // half-CTA tile-minor exchange: opt-in (PFFT_B200_HALFCTA=1), 512-thread tiles of 8 lines, blocked output,
+  // every chunk local (64-byte stores over NVLink reach 477 GB/s against 707 GB/s for 128 bytes and more)
+  static const int half_env = [] {
+    const char *e = getenv("PFFT_B200_HALFCTA");
+    return e ? atoi(e) : 0;
+  }();
+  sp.half_cta = (half_env && tl == 8 && THREADS == 64 && sp.oblk2 > 1 && sp.noseg == 1) ? 1 : 0;
+  const size_t pitch_x = N + (N >> 4) + (sp.half_cta ? 4 : 2);
   const size_t smem = (size_t)tl * N * 2 * sizeof(T) + tl * pitch_x * 8 + (size_t)TWN * 2 * sizeof(T) + 16;
   // contiguous pieces only: lines of a line-major input, block runs of a micro-blocked one
   if (sg.blocked ? sp.iblk2_stride != (long long)tl * sp.iblk2 : (sp.istride != 1 || sp.iseg_stride != 0)) return cudaErrorInvalidValue;

@@ -51,6 +51,7 @@ struct StageParams {
   // micro-blocked layouts / explicit tiles (core.h: Stage::iblk2 ...): handled by stage_blk_kernel
   int iblk2, oblk2, ntile;
   int iswz_mask, oswz_mask, oswz_shift, oswz_batch;
+  int half_cta;              // tile-minor exchange inside half-CTAs of tl/2 lines (stages without remote chunks)
   long long iblk2_stride, oblk2_stride;
   void *outp[16];            // out[out_seg[e]] + out_off[e], resolved at launch
   long long tile_ioff[kMaxTile], tile_ooff[kMaxTile];
