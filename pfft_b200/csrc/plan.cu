@@ -466,7 +466,7 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
 
 void plan_destroy(PlanBase *pl) {
   if (!pl) return;
-  if (pl->stream || true) cudaStreamSynchronize(pl->stream);
+  cudaStreamSynchronize(pl->stream);   // (the null stream too: kernels of this plan may still run)
   transport_teardown(pl);
   for (auto &e : pl->events) cudaEventDestroy(e);
   if (pl->fuse.ring) cudaFree(pl->fuse.ring);
