@@ -128,3 +128,76 @@ def test_shifted_semantics():
     Y = po.global_transform(po.C2C, x, n, flags=po.SHIFTED_IN | po.SHIFTED_OUT)
     want = np.fft.fftshift(np.fft.fftn(np.fft.ifftshift(x)))
     assert np.allclose(Y, want)
+
+
+# ---- embed / truncate conventions pinned on the reference's own kernel/ousample.c ----------
+def _stage_of_dim(kind, n, ni, no, flags, dim):
+    import pfft_b200 as pf
+    s = pf.describe_schedule(kind, n, [1, 1], 0, flags, ni, no, 1, None, None, +1 if kind == "c2r" else -1)
+    assert s["error"] == "", s["error"]
+    st = [g for g in s["stages"] if g["dim"] == dim and g["op"] != 0]
+    assert len(st) == 1
+    return st[0]
+
+
+def test_embed_truncate_windows_match_reference_code(built_lib, golden_dir):
+    """Every row the reference's embed / truncate loops produce (tests/golden/gen_ousam_golden.py) is what
+    the product planner's stage windows (nin, zin) / (nout, zout) describe -- including the padding of real
+    rows and the upper-end quirk of truncated r2c output and embedded c2r input."""
+    cases = _load(golden_dir, "ousam_embed_trunc.json")
+    assert len(cases) >= 60
+    S_IN, S_OUT, PAD = po.SHIFTED_IN, po.SHIFTED_OUT, po.PADDED_R2C
+    for c in cases:
+        trafo, op, hm, n0, n1i, n1o = c["trafo"], c["op"], c["howmany"], c["n0"], c["n1i"], c["n1o"]
+        kind = trafo.split("_")[0]
+        padded = trafo.endswith("padded")
+        embed = op == "embed"
+        n = [2, 2, n1o if embed else n1i]
+        ni = [2, 2, n1i] if embed else n
+        no = n if embed else [2, 2, n1o]
+        flags = (S_IN | S_OUT if c["shifted"] else 0) | (PAD if padded else 0)
+        g = _stage_of_dim(kind, n, ni, no, flags, 2)
+        pn = lambda v: v // 2 + 1     # noqa: E731  physical (complex) length of a real line's spectrum
+        # element width in reals and row lengths in elements on both sides of the reference's 1-D operation
+        if kind == "c2c":
+            w, row_i, row_o = 2 * hm, n1i, n1o
+        elif kind == "r2c" and embed:          # real input rows; the output rows carry the r2c padding
+            w, row_i, row_o = hm, (2 * pn(n1i) if padded else n1i), 2 * pn(n1o)
+        elif kind == "r2c":                    # half spectra
+            w, row_i, row_o = 2 * hm, pn(n1i), pn(n1o)
+        elif embed:                            # c2r, half spectra
+            w, row_i, row_o = 2 * hm, pn(n1i), pn(n1o)
+        else:                                  # c2r output rows: padding removed unless PADDED
+            w, row_i, row_o = hm, 2 * pn(n1i), (2 * pn(n1o) if padded else n1o)
+        if embed:
+            cnt, off = g["nin"], g["zin"]
+        else:
+            cnt, off = g["nout"], g["zout"]
+        src = np.arange(1, n0 * row_i * w + 1, dtype=np.float64).reshape(n0, row_i, w)
+        want = np.full((n0, row_o, w), np.nan)
+        if embed:
+            total = n1o if kind != "c2r" else pn(n1o)          # the length-n line the window sits in
+            want[:, :total, :] = 0.0
+            want[:, off:off + cnt, :] = src[:, :cnt, :]
+        else:
+            want[:, :cnt, :] = src[:, off:off + cnt, :]
+        got = np.asarray(c["out"][:want.size]).reshape(want.shape)
+        written = ~np.isnan(want)
+        assert np.array_equal(got[written], want[written]), (c["trafo"], op, c["shifted"], n0, n1i, n1o, hm, g["nin"], g["zin"], g["nout"], g["zout"])
+        assert np.all(got[~written] == -7.0)       # the reference leaves the padding of real rows untouched
+
+
+def test_embed_truncate_golden_is_current_if_reference_present(golden_dir):
+    import refint
+    if not (refint.available() and os.path.isdir("/root/reference")):
+        pytest.skip("oracle/_ref not built here")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_ousam", os.path.join(golden_dir, "gen_ousam_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    lib = refint.RefInt().lib
+    c = _load(golden_dir, "ousam_embed_trunc.json")[5]
+    trafo = {"c2c": gen.C2C, "r2c": gen.R2C, "r2c_padded": gen.R2C | gen.PADDED, "c2r": gen.C2R, "c2r_padded": gen.C2R | gen.PADDED}[c["trafo"]]
+    out = gen.run_case(lib, trafo, gen.EMBED if c["op"] == "embed" else gen.TRUNC, (gen.S_IN | gen.S_OUT) if c["shifted"] else 0,
+                       c["n0"], c["n1i"], c["n1o"], c["howmany"])
+    assert out == c["out"]
