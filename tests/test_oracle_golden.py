@@ -201,3 +201,37 @@ def test_embed_truncate_golden_is_current_if_reference_present(golden_dir):
     out = gen.run_case(lib, trafo, gen.EMBED if c["op"] == "embed" else gen.TRUNC, (gen.S_IN | gen.S_OUT) if c["shifted"] else 0,
                        c["n0"], c["n1i"], c["n1o"], c["howmany"])
     assert out == c["out"]
+
+
+# ---- PFFT_SHIFTED_IN / _OUT modulations pinned on the reference's own twiddle code ----------
+def test_shift_modulations_match_reference_code(built_lib, golden_dir):
+    """The +-1 factor of EVERY element as the reference's twiddle_input / twiddle_output compute it
+    (tests/golden/gen_shift_golden.py) equals the product of the per-dimension modulations the planner fuses
+    into the stage that transforms that dimension (Stage::mod_in / mod_out) -- pruned sizes, skipped
+    transforms, both-sides-shifted extra sign and transposed memory order included."""
+    import pfft_b200 as pf
+    cases = _load(golden_dir, "shift_twiddles.json")
+    assert len(cases) >= 60
+    for c in cases:
+        n, nio, out_side = c["n"], c["nio"], c["output_side"]
+        tflag = (po.TRANSPOSED_OUT if out_side else po.TRANSPOSED_IN) if c["transposed"] else 0
+        ni, no = (n, nio) if out_side else (nio, n)
+        s = pf.describe_schedule("c2c", n, [1, 1], 0, c["flags"] | tflag, ni, no, 1, None, None, -1, None, c["skip"])
+        assert s["error"] == "", s["error"]
+        vecs = []
+        for t in range(3):
+            f = np.ones(nio[t])
+            for g in s["stages"]:
+                if g["dim"] != t or g["op"] == 0:
+                    continue
+                on, start, half, extra = g["mod_out"] if out_side else g["mod_in"]
+                assert (g["nout"] if out_side else g["nin"]) == nio[t]
+                if on:
+                    idx = np.arange(nio[t]) + start
+                    f = np.where(idx < half, np.where(idx % 2 != 0, -1.0, 1.0) * extra, 1.0)
+            vecs.append(f)
+        full = vecs[0][:, None, None] * vecs[1][None, :, None] * vecs[2][None, None, :]
+        if c["transposed"]:
+            full = full.transpose(1, 2, 0)          # memory order of a transposed layout on a 2-D mesh
+        want = np.asarray(c["factors"], dtype=np.float64).reshape(full.shape)
+        assert np.array_equal(full, want), {k: v for k, v in c.items() if k != "factors"}
