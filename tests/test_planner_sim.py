@@ -157,3 +157,69 @@ def test_illegal_combinations_are_refused(built_lib):
     assert pf.describe_schedule("c2r", [8, 8, 8], [2, 2], 0, T_OUT)["error"].startswith("illegal")
     assert pf.describe_schedule("c2c", [9, 8, 8], [2, 2], 0, S_IN)["error"].startswith("illegal")
     assert pf.describe_schedule("c2c", [8, 8], [2, 2], 0, 0)["error"].startswith("illegal")
+
+
+def _random_cases(count, seed):
+    """Legal random configurations (sizes, pruning, meshes, flags, kinds) -- the planner must either produce a
+    schedule that reproduces the oracle or say that the configuration is unsupported."""
+    import random
+    rnd = random.Random(seed)
+    meshes = [[1], [2], [3], [1, 1], [2, 1], [1, 2], [2, 2], [3, 2], [2, 3], [2, 2, 2], [1, 2, 2]]
+    out = []
+    while len(out) < count:
+        np_ = rnd.choice(meshes)
+        r = len(np_)
+        d = rnd.choice([x for x in (2, 3, 4) if x > r or (x == r == 3)])
+        kind = rnd.choice(["c2c", "c2c", "r2c", "c2r", "r2r"])
+        shifted = rnd.random() < 0.25 and kind in ("c2c",)
+        n = [rnd.choice([4, 6, 8, 10, 12] if shifted else [3, 4, 5, 6, 7, 8, 9, 12]) for _ in range(d)]
+        case = dict(kind=kind, n=n, np=np_)
+        flags = 0
+        tr = rnd.choice([0, T_OUT, T_IN])
+        if kind == "r2c" and tr == T_IN:
+            tr = T_OUT
+        if kind == "c2r" and tr == T_OUT:
+            tr = T_IN
+        flags |= tr
+        if d == r:          # 3-D data on a 3-D mesh: no padded real rows
+            pass
+        elif kind in ("r2c", "c2r") and rnd.random() < 0.3:
+            flags |= PAD
+        if shifted:
+            flags |= rnd.choice([S_IN, S_OUT, S_IN | S_OUT])
+        if rnd.random() < 0.3 and d > r:
+            even = 2 if shifted else 1
+            ni = [max(2, (x - rnd.randint(0, x // 2)) // even * even) for x in n]
+            no = [max(2, (x - rnd.randint(0, x // 2)) // even * even) for x in n]
+            if kind == "r2c":
+                case["ni"], case["no"] = ni, n
+            elif kind == "c2r":
+                case["ni"], case["no"] = n, no
+            else:
+                case["ni"], case["no"] = ni, no
+        if kind == "c2c":
+            case["sign"] = rnd.choice([-1, +1])
+            if rnd.random() < 0.2 and d > r:
+                case["howmany"] = rnd.choice([2, 3])
+        if kind == "c2r":
+            case["sign"] = +1
+        if kind == "r2r":
+            case["kinds"] = [rnd.choice([po.REDFT00, po.REDFT01, po.REDFT10, po.REDFT11, po.RODFT00, po.RODFT01,
+                                         po.RODFT10, po.RODFT11]) for _ in range(d)]
+            case["n"] = [max(x, 3) for x in n]
+        case["flags"] = flags
+        out.append(case)
+    return out
+
+
+@pytest.mark.parametrize("case", _random_cases(60, 20261017), ids=lambda c: "%s-%s-np%s-f%d%s" % (
+    c["kind"], "x".join(map(str, c["n"])), "x".join(map(str, c["np"])), c.get("flags", 0), "-pruned" if "ni" in c else ""))
+def test_random_configurations_reproduce_oracle(built_lib, case):
+    P = int(np.prod(case["np"]))
+    s0 = pf.describe_schedule(case["kind"], case["n"], case["np"], 0, case.get("flags", 0), case.get("ni"), case.get("no"),
+                              case.get("howmany", 1), None, None, case.get("sign", -1), case.get("kinds"), None)
+    if s0["error"].startswith("illegal") or "not supported" in s0["error"]:
+        pytest.skip(s0["error"])
+    err, scheds = run_virtual(case)
+    assert len(scheds) == P
+    assert err < 1e-12, err
