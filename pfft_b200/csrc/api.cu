@@ -63,6 +63,12 @@ INT local_size_impl(Kind kind, int rnk_n, const INT *n, const INT *ni, const INT
                     INT *lno, INT *los) {
   int rank = 0;
   Problem p = make_problem(kind, rnk_n, n, ni, no, howmany, iblock, oblock, comm, -1, nullptr, nullptr, flags, &rank);
+  if (p.rnk_n < 1 || p.rnk_n > kMaxDims - 1 || p.rnk_pm < 1 || p.rnk_pm > kMaxMesh) {
+    // fixed-size arrays behind the integer layer: refuse rather than overrun them
+    set_error("pfft_local_size: rnk_n must be 1..7 and the process mesh at most 3-dimensional");
+    for (int t = 0; t < rnk_n; t++) lni[t] = lis[t] = lno[t] = los[t] = 0;
+    return 0;
+  }
   LocalSizes ls;
   local_block(p, rank, &ls);
   for (int t = 0; t < rnk_n; t++) {
@@ -77,6 +83,11 @@ INT local_size_impl(Kind kind, int rnk_n, const INT *n, const INT *ni, const INT
 void local_block_impl(Kind kind, int rnk_n, const INT *ni, const INT *no, const INT *iblock, const INT *oblock,
                       MPI_Comm comm, int pid, unsigned flags, INT *lni, INT *lis, INT *lno, INT *los) {
   Problem p = make_problem(kind, rnk_n, ni, ni, no, 1, iblock, oblock, comm, -1, nullptr, nullptr, flags, nullptr);
+  if (p.rnk_n < 1 || p.rnk_n > kMaxDims - 1 || p.rnk_pm < 1 || p.rnk_pm > kMaxMesh) {
+    set_error("pfft_local_block: rnk_n must be 1..7 and the process mesh at most 3-dimensional");
+    for (int t = 0; t < rnk_n; t++) lni[t] = lis[t] = lno[t] = los[t] = 0;
+    return;
+  }
   LocalSizes ls;
   local_block(p, pid, &ls);
   for (int t = 0; t < rnk_n; t++) {
@@ -694,6 +705,15 @@ size_t pfftb200_plan_describe(const void *plan, char *buf, size_t buflen) {
   for (size_t i = 0; i < pl->use_pow2.size(); i++) {
     k += i ? "," : "";
     k += pl->use_pow2[i] ? "\"pow2\"" : "\"generic\"";
+  }
+  k += "],\"kernel_names\":[";
+  for (size_t i = 0; i < pl->params.size(); i++) {
+    // the __global__ function the launchers pick for this stage (fft_pow2.cu: launch_stage_pow2 / launch_block_class)
+    const StageParams &sp = pl->params[i];
+    const char *nm = "stage_generic_kernel";
+    if (pl->use_pow2[i]) nm = sp.ntile > 0 ? "stage_blk_kernel" : ((sp.fast && sp.istride == 1) ? "fused_pair_kernel<FUSED=false>" : "stage_pow2_kernel");
+    k += i ? "," : "";
+    k += std::string("\"") + nm + "\"";
   }
   k += "],\"tile_lines\":[";
   for (size_t i = 0; i < pl->params.size(); i++) k += (i ? "," : "") + std::to_string(pl->params[i].tl);

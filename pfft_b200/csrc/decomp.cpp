@@ -72,6 +72,9 @@ bool problem_is_legal(const Problem &p, std::string *why) {
     return false;
   };
   const unsigned tr = p.flags & (F_TRANSPOSED_IN | F_TRANSPOSED_OUT);
+  // limits of this implementation (fixed-size arrays in Problem / LocalSizes); the reference takes any rnk_pm < rnk_n
+  if (p.rnk_n < 1 || p.rnk_n > kMaxDims - 1) return fail("rnk_n outside 1..7 is not supported");
+  if (p.rnk_pm < 1 || p.rnk_pm > kMaxMesh) return fail("process meshes of more than 3 dimensions are not supported");
   if (p.flags & (F_SHIFTED_IN | F_SHIFTED_OUT))
     for (int t = 0; t < p.rnk_n; t++)
       if (p.n[t] % 2) return fail("index shift needs even n");

@@ -394,7 +394,11 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
         if (!FAST && sp.in_real) im = 0;
         if (c2r_line && t_in + e * THREADS - sp.zin > N / 2) im = -im;
         if (!FAST && sp.mod_in.on) {
-          if (sign_mod_dev(sp.mod_in, t_in + e * THREADS - sp.zin) < 0) { re = -re; im = -im; }
+          // the modulation belongs to the element as stored (reference api/api-basic.c twiddle_input acts on the
+          // half spectrum before it is completed): a mirrored c2r bin takes the factor of its source index
+          int jm = t_in + e * THREADS - sp.zin;
+          if (c2r_line && jm > N / 2) jm = N - jm;
+          if (sign_mod_dev(sp.mod_in, jm) < 0) { re = -re; im = -im; }
         }
         x[e].x = backward ? im : re;
         x[e].y = backward ? re : im;

@@ -118,6 +118,12 @@ struct Builder {
         s.error = "PFFT_PADDED_R2C/C2R is not supported for 3-D data on a 3-D process mesh";
         return false;
       }
+      if (p.has_iblock || p.has_oblock) {
+        // the reference feeds them to the blocks of the remapped mesh, where they have no meaning
+        // (kernel/remap_3dto2d.c:36 "TODO: implement user blocksize"); refuse instead of misplacing data
+        s.error = "user block sizes are not supported for 3-D data on a 3-D process mesh";
+        return false;
+      }
       mesh_coords(3, p.np, s.pid, c3);
       r = 2;
       np[0] = p.np[0] * m3.q0;

@@ -57,8 +57,9 @@ def oracle_output(case, xg):
                                case.get("flags", 0), case.get("kinds"), skip_dims)
 
 
-def compare_local_output(case, want, flat, lno, los, rnk_pm):
-    """max abs error of one rank's flattened output block against the oracle's global result."""
+def compare_local_output(case, want, flat, lno, los, rnk_pm, sumsq=False):
+    """max abs error of one rank's flattened output block against the oracle's global result
+    (with sumsq=True: (max abs error, sum of squared errors) -- for the relative L2 error of the whole array)."""
     kind, n, flags = case["kind"], case["n"], case.get("flags", 0)
     no = case.get("no") or n
     hm = case.get("howmany", 1)
@@ -69,7 +70,7 @@ def compare_local_output(case, want, flat, lno, los, rnk_pm):
     order = po.mem_order(d, rnk_pm, True) if tout else list(range(d))
     shp = [lno[t] for t in order] + ([hm] if hm > 1 else [])
     if int(np.prod(shp)) == 0:
-        return 0.0
+        return (0.0, 0.0) if sumsq else 0.0
     got = np.asarray(flat)[:int(np.prod(shp))].reshape(shp)
     ln = list(lno)
     if kind == "c2r" and lno[-1] != no[-1] and rnk_pm < d:      # padded real rows: compare the logical part
@@ -79,4 +80,7 @@ def compare_local_output(case, want, flat, lno, los, rnk_pm):
     inv = np.argsort(order).tolist()
     got = np.transpose(got, inv + list(range(d, got.ndim)))
     ref = po.extract_block(want, ln, los, None, shift)
-    return float(np.abs(got - ref).max()) if ref.size else 0.0
+    if not ref.size:
+        return (0.0, 0.0) if sumsq else 0.0
+    diff = np.abs(got - ref).astype(np.float64)
+    return (float(diff.max()), float((diff ** 2).sum())) if sumsq else float(diff.max())

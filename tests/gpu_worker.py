@@ -81,20 +81,27 @@ def run_case(case, comm, seed=0):
         ma_in.free()
         if not inplace:
             ma_out.free()
-    return dict(error="", local_ni=lni, local_i_start=lis, local_no=lno, local_o_start=los, out=out,
-                input_preserved=preserved, kernels=desc["kernels"], transport=desc["transport"],
+    dev = pf.lib().pfftb200_get_device()
+    return dict(error="", local_ni=lni, local_i_start=lis, local_no=lno, local_o_start=los, out=out, device=int(dev),
+                input_preserved=preserved, kernels=desc["kernels"], kernel_names=desc.get("kernel_names", []),
+                transport=desc["transport"],
                 fused=desc.get("fused_active", 0))
 
 
-def check_case(case, results):
-    """results: list over ranks of run_case dicts -> relative max error vs the oracle."""
+def check_case(case, results, l2=False):
+    """results: list over ranks of run_case dicts -> relative max error vs the oracle; with l2=True
+    (relative max error, relative L2 error of the whole gathered array -- the north_star's metric)."""
     xg = cases.make_global_input(case, 0)
     want = cases.oracle_output(case, xg)
     scale = max(1e-300, float(np.abs(want).max()))
     r = len(case["np"])
-    err = 0.0
+    err, ssq = 0.0, 0.0
     for res in results:
-        err = max(err, cases.compare_local_output(case, want, res["out"], res["local_no"], res["local_o_start"], r))
+        m, s2 = cases.compare_local_output(case, want, res["out"], res["local_no"], res["local_o_start"], r, sumsq=True)
+        err = max(err, m)
+        ssq += s2
+    if l2:
+        return err / scale, float(np.sqrt(ssq) / max(1e-300, np.linalg.norm(np.asarray(want, dtype=np.complex128).ravel())))
     return err / scale
 
 
