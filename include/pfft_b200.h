@@ -65,6 +65,16 @@ unsigned long long pfftb200_launch_count(void);
 void pfftb200_enable_stage_timing(const void *plan, int on);
 int pfftb200_stage_times(const void *plan, double *ms, int max_stages);
 
+
+/* TEST SUPPORT (tests/test_kernel_emulation.py): stage `stage` of rank `pid`'s schedule run through the body
+ * of the any-length CUDA stage kernel on the CPU -- the same host+device source the GPU executes, threads
+ * emulated between barriers -- on host buffers.  prec 0: double, 1: float.  Nothing in the library calls this;
+ * it is not a CPU fallback.  Returns 0 on success. */
+int pfftb200_emulate_stage(int prec, int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                           ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                           const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                           unsigned pfft_flags, int stage, const void *in, void *const *outs);
+
 #ifdef __cplusplus
 }
 #endif

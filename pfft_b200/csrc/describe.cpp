@@ -1,10 +1,13 @@
 // describe.cpp -- MPI-free, CUDA-free entry points over the integer layer and the planner
 // (include/pfft_b200.h): used by tests to enumerate every rank of a mesh in one process.
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
+#include <vector>
 
 #include "core.h"
+#include "kernels.h"
 #include "pfft_b200.h"
 
 namespace pfb {
@@ -41,13 +44,63 @@ void fill_problem(Problem *p, int kind, int rnk_n, const INT *n, const INT *ni, 
 }
 }  // namespace pfb
 
+namespace pfb { void set_error(const std::string &msg); }
 using namespace pfb;
+
+namespace {
+struct HostTables {
+  std::vector<void *> ptrs;
+  ~HostTables() {
+    for (void *p : ptrs) free(p);
+  }
+};
+void *upload_host(const void *host, size_t bytes, void *ctx) {
+  void *p = malloc(bytes ? bytes : 1);
+  memcpy(p, host, bytes);
+  static_cast<HostTables *>(ctx)->ptrs.push_back(p);
+  return p;
+}
+template <typename T>
+int emulate_stage(const Stage &g, const void *in, void *const *outs) {
+  StageParams sp;
+  std::string err;
+  HostTables tabs;
+  if (!stage_params_basic(g, sp, &err)) { set_error(err); return 1; }
+  if (g.ntile > 0 || g.iblk2 > 1 || g.oblk2 > 1) { set_error("micro-blocked stages belong to the register-resident kernel"); return 2; }
+  if (g.op == OP_R2R) sp.tw_r2r = make_r2r_table<T>(sp.r2r_D, upload_host, &tabs);
+  if (!mixed_prepare<T>(g, sp, upload_host, &tabs, &err)) { set_error(err); return 1; }
+  stage_params_tiles(g, sp, sp.tl);
+  sp.in = in;
+  for (int q = 0; q < g.noseg; q++) sp.out[q] = outs[q];
+  sp.mx.gws = 0;
+  emulate_stage_mixed<T>(sp);
+  return 0;
+}
+}  // namespace
 
 extern "C" {
 
 const char *pfftb200_version(void) { return "pfft_b200 0.1 (sm_100a)"; }
 
 const char *pfftb200_last_error(void) { return last_error_ref().c_str(); }
+
+
+// TEST SUPPORT: run stage `stage` of rank `pid`'s schedule through the BODY OF THE CUDA KERNEL
+// (fft_mixed.h, the code stage_mixed_kernel executes) on the CPU, threads emulated one after the other
+// between barriers.  `in`: the stage's input buffer, `outs`: one buffer per output chunk (host memory).
+// prec 0: fp64, 1: fp32.  Returns 0, or non-zero with pfftb200_last_error() set.  Not a CPU fallback:
+// nothing in the library calls it.
+int pfftb200_emulate_stage(int prec, int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                           ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm, const int *np,
+                           int pid, int sign, const int *kinds, const int *skip_trafos, unsigned pfft_flags, int stage,
+                           const void *in, void *const *outs) {
+  Problem p;
+  fill_problem(&p, kind, rnk_n, n, ni, no, howmany, iblock, oblock, rnk_pm, np, sign, kinds, skip_trafos, pfft_flags);
+  Schedule s;
+  if (!build_schedule(p, pid, &s)) { set_error(s.error); return 1; }
+  if (stage < 0 || stage >= (int)s.stages.size()) { set_error("no such stage"); return 1; }
+  return prec == 0 ? emulate_stage<double>(s.stages[stage], in, outs) : emulate_stage<float>(s.stages[stage], in, outs);
+}
 
 size_t pfftb200_describe_schedule(int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
                                   ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,

@@ -1223,8 +1223,14 @@ int points_per_thread(int n) { return pow2_points_per_thread(n); }   // core.h: 
 template <typename T>
 bool pow2_supported(const Stage &g, int L) {
   if (L < 64 || L > 4096 || (L & (L - 1))) return false;
-  // real lines run as a full-length complex transform: r2c with imaginary parts zero (the kept outputs are
-  // the first n/2+1), c2r with the upper half of the spectrum completed by Hermitian symmetry on load
+  // Real lines: the any-length kernel runs them as n/2 packed complex points (fft_mixed.h).  The path below
+  // (full-length complex transform: r2c with imaginary parts zero, c2r with the upper half of the spectrum
+  // completed by Hermitian symmetry on load) is kept behind PFFT_B200_REAL_POW2=1 for comparison.
+  static const bool real_pow2 = [] {
+    const char *e = getenv("PFFT_B200_REAL_POW2");
+    return e && atoi(e) != 0;
+  }();
+  if ((g.op == OP_R2C || g.op == OP_C2R) && !real_pow2) return false;
   if (g.op == OP_R2C) {
     if (!g.in_real || g.out_real) return false;
   } else if (g.op == OP_C2R) {

@@ -4,6 +4,7 @@
 // the kernels never call sincos (fp64 accuracy target: 1e-12 relative L2 over a
 // 1024^3 transform, BASELINE.json north_star).
 #include <math.h>
+#include <string.h>
 
 #include "kernels.h"
 
@@ -65,6 +66,74 @@ void make_twiddles_f32(int L, float *re_im) {
     re_im[2 * k] = (float)c;
     re_im[2 * k + 1] = (float)s;
   }
+}
+
+// Fields of a stage every kernel reads (plain copies of the planner's Stage; lengths, windows, strides,
+// batch walk, tile table).  Tile geometry (tl, ntiles) is filled in by stage_params_tiles once the kernel
+// family has chosen its lines per tile.
+bool stage_params_basic(const Stage &g, StageParams &sp, std::string *err) {
+  memset(&sp, 0, sizeof sp);
+  if (g.n > (1 << 22)) {
+    *err = "transform length too large";
+    return false;
+  }
+  int L = (int)g.n;
+  if (g.op == OP_R2R) {
+    // DCT/DST line of n reals = zero-padded complex DFT of length 2D between two twiddles (kernels.h)
+    if (!r2r_params(g.r2r_kind, (int)g.n, &sp.r2r_a2, &sp.r2r_b2, &sp.r2r_D, &sp.r2r_sine, &sp.r2r_half0, &sp.r2r_halfn)) {
+      *err = "r2r kind " + std::to_string(g.r2r_kind) + " on length " + std::to_string(g.n) +
+             " is not supported (DCT/DST kinds REDFT00..RODFT11 only)";
+      return false;
+    }
+    L = 2 * sp.r2r_D;
+  }
+  sp.op = g.op;
+  sp.sign = g.sign;
+  sp.r2r_kind = g.r2r_kind;
+  sp.n = (int)g.n;
+  sp.L = L;
+  sp.nin = (int)g.nin; sp.zin = (int)g.zin; sp.nout = (int)g.nout; sp.zout = (int)g.zout;
+  sp.istride = g.istride; sp.iseg_stride = g.iseg_stride; sp.iblk = (int)g.iblk;
+  sp.ostride = g.ostride; sp.oblk = (int)g.oblk; sp.noseg = g.noseg;
+  sp.nbatch = g.nbatch;
+  for (int k = 0; k < g.nbatch; k++) {
+    sp.bext[k] = g.batch[k].extent;
+    sp.bis[k] = g.batch[k].istride;
+    sp.bos[k] = g.batch[k].ostride;
+  }
+  sp.tile_dim = g.tile_dim;
+  sp.iblk2 = (int)g.iblk2; sp.iblk2_stride = g.iblk2_stride;
+  sp.oblk2 = (int)g.oblk2; sp.oblk2_stride = g.oblk2_stride;
+  sp.ntile = g.ntile;
+  sp.iswz_mask = g.iswz_mask; sp.oswz_mask = g.oswz_mask; sp.oswz_shift = g.oswz_shift; sp.oswz_batch = g.oswz_batch;
+  for (int l = 0; l < g.ntile; l++) { sp.tile_ioff[l] = g.tile_ioff[l]; sp.tile_ooff[l] = g.tile_ooff[l]; }
+  sp.in_real = g.in_real; sp.out_real = g.out_real; sp.conj_in = g.conj_in; sp.conj_out = g.conj_out;
+  sp.mod_in = {g.mod_in.on, (int)g.mod_in.start, (int)g.mod_in.half, g.mod_in.extra};
+  sp.mod_out = {g.mod_out.on, (int)g.mod_out.start, (int)g.mod_out.half, g.mod_out.extra};
+  return true;
+}
+
+void stage_params_tiles(const Stage &g, StageParams &sp, int tl) {
+  long long lines = 1;
+  for (int k = 0; k < g.nbatch; k++) lines *= g.batch[k].extent;
+  if (g.in_elems == 0 && g.nin > 0) lines = 0;   // some batch extent of size 1 was dropped but another is 0
+  sp.tl = tl;
+  if (g.tile_dim >= 0) {
+    long long others = 1;
+    for (int k = 0; k < g.nbatch; k++)
+      if (k != g.tile_dim) others *= g.batch[k].extent;
+    sp.tiles_along = (g.batch[g.tile_dim].extent + tl - 1) / tl;
+    sp.ntiles = others * sp.tiles_along;
+  } else {
+    sp.tiles_along = 1;
+    sp.ntiles = lines;
+  }
+  if (g.ntile > 0) {
+    // explicit tiles: batch[] enumerates them (`lines` is their number here)
+    sp.tiles_along = 1;
+    sp.ntiles = lines;
+  }
+  if (g.nout == 0 || lines == 0) sp.ntiles = 0;
 }
 
 unsigned long long &launch_counter() {

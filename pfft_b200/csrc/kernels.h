@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
 #include <vector>
 
 #include "core.h"
@@ -13,6 +14,45 @@ constexpr int kMaxFactors = 24;
 
 struct SignModDev {
   int on, start, half, extra;
+};
+
+// x / d for a run-time constant d (round-up method, exact for 32-bit x)
+struct FastDiv {
+  unsigned m, s1, s2;
+};
+inline FastDiv make_fastdiv(unsigned d) {
+  FastDiv f;
+  unsigned l = 0;
+  while ((1ull << l) < d) l++;
+  f.m = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+
+// any-length stage kernel (fft_mixed.h / fft_mixed.cu)
+constexpr int kMaxMixedPass = 24;
+struct MixedPass {
+  int R, LR, Ns, tstep;      // radix, butterflies per line (Lc / R), product of earlier radices, twiddle table step
+  FastDiv dLR, dNs;
+};
+struct MixedParams {
+  int L;                     // complex points of a line: n, n/2 for even-length real lines, 2D for DCT/DST
+  int Lc;                    // length of the transforms actually run: L, or the Bluestein length M >= 2L - 1
+  int half_real;             // 0: complex line, 1: r2c on n/2 packed points, 2: c2r on n/2 packed points
+  int bluestein, swap, zero_fill;
+  int pitch;                 // complex elements per buffer line (padded)
+  int tl_shift;              // log2(tl)
+  int gws;                   // buffers live in the global workspace (line does not fit shared memory)
+  int npass;
+  MixedPass pass[kMaxMixedPass];
+  FastDiv dnin, dnout, diblk, doblk, dL, dLc;
+  const void *tw;            // Lc entries exp(-2 pi i k / Lc)
+  const void *tw_half;       // n/2 + 1 entries exp(-2 pi i k / n) (packed real lines)
+  const void *chirp;         // Bluestein: L entries exp(-i pi j^2 / L)
+  const void *bhat;          // Bluestein: Lc entries FFT(conj chirp, wrapped) / Lc
+  void *ws;                  // global workspace
+  long long ws_stride;       // complex elements per CTA
 };
 
 // Plain-old-data copy of a Stage plus pointers; passed to kernels by value.
@@ -58,6 +98,7 @@ struct StageParams {
   long long in_off[16];      // element offset of line index e*THREADS on input
   long long out_off[16];     // ... on output, inside chunk out_seg[e]
   int out_seg[16];
+  MixedParams mx;
 };
 
 // Plane-fused pair of stages (fft_pow2.cu: fused_pair_kernel).
@@ -72,6 +113,8 @@ struct FusePlanes {
 };
 
 // host-side helpers (fft_tables.cpp)
+bool stage_params_basic(const Stage &g, StageParams &sp, std::string *err);
+void stage_params_tiles(const Stage &g, StageParams &sp, int tl);
 int factorize_generic(int L, int *fac);
 // parameters of an r2r kind (FFTW's enum values) on a line of n reals; false: unsupported kind
 bool r2r_params(int kind, int n, int *a2, int *b2, int *D, int *sine, int *half0, int *halfn);          // radices for the generic shared-memory kernel
@@ -83,6 +126,18 @@ template <typename T>
 cudaError_t launch_stage_generic(StageParams &sp, cudaStream_t stream);
 template <typename T>
 int generic_pick_tile(const Stage &g, int L);    // lines per tile (0: does not fit in shared memory)
+
+// any-length stage kernel (fft_mixed.cu).  `upload` copies a host table to where the kernel will read it
+// (device memory for the real thing, host memory for the CPU emulation of the kernel body).
+using UploadFn = void *(*)(const void *host, size_t bytes, void *ctx);
+template <typename T>
+bool mixed_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, std::string *err);
+template <typename T>
+cudaError_t launch_stage_mixed(StageParams &sp, void **ws, size_t *ws_bytes, cudaStream_t stream);
+template <typename T>
+void emulate_stage_mixed(StageParams &sp);      // the kernel body on the CPU (tests only)
+template <typename T>
+void *make_r2r_table(int D, UploadFn upload, void *ctx);   // plan.cu
 
 // fast path: power-of-two complex lines held in registers (fft_pow2.cu)
 template <typename T>

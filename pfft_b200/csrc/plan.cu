@@ -86,134 +86,101 @@ static bool all_ranks_ok(MPI_Comm comm, bool ok) {
   return all != 0;
 }
 
+static void *upload_device(const void *host, size_t bytes, void *ctx) {
+  PlanBase *pl = static_cast<PlanBase *>(ctx);
+  void *dev = nullptr;
+  CUDA_OK(cudaMalloc(&dev, bytes));
+  CUDA_OK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
+  pl->tables.push_back(dev);
+  return dev;
+}
+
+// table exp(-2 pi i m / (8 D)) of the DCT/DST pre- and post-twiddles (kernels.h)
+template <typename T>
+void *make_r2r_table(int D, UploadFn upload, void *ctx) {
+  const int M = 8 * D;
+  std::vector<double> roots(2 * (size_t)M);
+  make_twiddles_f64(M, roots.data());
+  std::vector<T> host(roots.begin(), roots.end());
+  return upload(host.data(), host.size() * sizeof(T), ctx);
+}
+template void *make_r2r_table<float>(int, UploadFn, void *);
+template void *make_r2r_table<double>(int, UploadFn, void *);
+
+// Kernel family of every stage and its parameters:
+//   pow2   power-of-two complex lines, 64..4096, held in registers (fft_pow2.cu; the headline path)
+//   mixed  everything else: any length, real lines, DCT/DST, copy stages (fft_mixed.cu)
+//   generic  the round-1 any-length kernel, kept behind PFFT_B200_GENERIC=1 for A/B comparisons
 template <typename T>
 static bool build_stage_params(PlanBase *pl, std::string *err) {
   struct TableSet {
     void *dev;
     size_t off2, off3;
-    bool has_pow2;
   };
   std::map<int, TableSet> table_of;
+  static const bool old_generic = [] {
+    const char *e = getenv("PFFT_B200_GENERIC");
+    return e && atoi(e) != 0;
+  }();
   const Schedule &s = pl->sched;
   for (size_t i = 0; i < s.stages.size(); i++) {
     const Stage &g = s.stages[i];
     StageParams sp;
-    memset(&sp, 0, sizeof sp);
-    if (g.n > (1 << 22)) {
-      *err = "transform length too large";
-      return false;
-    }
-    int L = (int)g.n;
-    if (g.op == OP_R2R) {
-      // DCT/DST line of n reals = zero-padded complex DFT of length 2D between two twiddles (kernels.h)
-      if (!r2r_params(g.r2r_kind, (int)g.n, &sp.r2r_a2, &sp.r2r_b2, &sp.r2r_D, &sp.r2r_sine, &sp.r2r_half0, &sp.r2r_halfn)) {
-        *err = "r2r kind " + std::to_string(g.r2r_kind) + " on length " + std::to_string(g.n) +
-               " is not supported (DCT/DST kinds REDFT00..RODFT11 only)";
-        return false;
-      }
-      L = 2 * sp.r2r_D;
-    }
-    sp.op = g.op;
-    sp.sign = g.sign;
-    sp.r2r_kind = g.r2r_kind;
-    sp.n = (int)g.n;
-    sp.L = L;
-    sp.nin = (int)g.nin; sp.zin = (int)g.zin; sp.nout = (int)g.nout; sp.zout = (int)g.zout;
-    sp.istride = g.istride; sp.iseg_stride = g.iseg_stride; sp.iblk = (int)g.iblk;
-    sp.ostride = g.ostride; sp.oblk = (int)g.oblk; sp.noseg = g.noseg;
-    sp.nbatch = g.nbatch;
-    long long lines = 1;
-    for (int k = 0; k < g.nbatch; k++) {
-      sp.bext[k] = g.batch[k].extent;
-      sp.bis[k] = g.batch[k].istride;
-      sp.bos[k] = g.batch[k].ostride;
-      lines *= g.batch[k].extent;
-    }
-    if (g.in_elems == 0 && g.nin > 0) lines = 0;   // some batch extent of size 1 was dropped but another is 0
-    sp.tile_dim = g.tile_dim;
-    sp.iblk2 = (int)g.iblk2; sp.iblk2_stride = g.iblk2_stride;
-    sp.oblk2 = (int)g.oblk2; sp.oblk2_stride = g.oblk2_stride;
-    sp.ntile = g.ntile;
-    sp.iswz_mask = g.iswz_mask; sp.oswz_mask = g.oswz_mask; sp.oswz_shift = g.oswz_shift; sp.oswz_batch = g.oswz_batch;
-    for (int l = 0; l < g.ntile; l++) { sp.tile_ioff[l] = g.tile_ioff[l]; sp.tile_ooff[l] = g.tile_ooff[l]; }
-    sp.in_real = g.in_real; sp.out_real = g.out_real; sp.conj_in = g.conj_in; sp.conj_out = g.conj_out;
-    sp.mod_in = {g.mod_in.on, (int)g.mod_in.start, (int)g.mod_in.half, g.mod_in.extra};
-    sp.mod_out = {g.mod_out.on, (int)g.mod_out.start, (int)g.mod_out.half, g.mod_out.extra};
+    if (!stage_params_basic(g, sp, err)) return false;
+    const int L = sp.L;
     const bool fast = pow2_supported<T>(g, L);
-    int tl = fast ? pow2_pick_tile<T>(g, L) : generic_pick_tile<T>(g, L);
-    if (tl <= 0) {
-      *err = "transform length " + std::to_string(L) + " does not fit the shared-memory kernels yet";
-      return false;
+    int kind = fast ? KERNEL_POW2 : (old_generic ? KERNEL_GENERIC : KERNEL_MIXED);
+    if (g.op == OP_R2R) {
+      auto jt = table_of.find(-8 * sp.r2r_D);
+      if (jt == table_of.end()) jt = table_of.emplace(-8 * sp.r2r_D, TableSet{make_r2r_table<T>(sp.r2r_D, upload_device, pl), 0, 0}).first;
+      sp.tw_r2r = jt->second.dev;
     }
-    sp.tl = tl;
-    if (g.tile_dim >= 0) {
-      long long others = 1;
-      for (int k = 0; k < g.nbatch; k++)
-        if (k != g.tile_dim) others *= g.batch[k].extent;
-      sp.tiles_along = (g.batch[g.tile_dim].extent + tl - 1) / tl;
-      sp.ntiles = others * sp.tiles_along;
+    if (kind == KERNEL_MIXED) {
+      if (!mixed_prepare<T>(g, sp, upload_device, pl, err)) return false;
+      stage_params_tiles(g, sp, sp.tl);
     } else {
-      sp.tiles_along = 1;
-      sp.ntiles = lines;
-    }
-    if (g.ntile > 0) {
-      // explicit tiles: batch[] enumerates them (`lines` is their number here)
-      sp.tiles_along = 1;
-      sp.ntiles = lines;
-    }
-    if (g.nout == 0 || lines == 0) sp.ntiles = 0;
-    sp.nfac = factorize_generic(L, sp.fac);
-    if (g.op != OP_COPY) {
-      auto it = table_of.find(2 * L + (fast ? 1 : 0));
-      if (it == table_of.end()) {
-        // unit roots in fp64 (< 1 ulp), then the layouts the kernels want, rounded once to T
-        std::vector<double> roots(2 * (size_t)L);
-        make_twiddles_f64(L, roots.data());
-        std::vector<double> all(roots);
-        size_t off2 = 0, off3 = 0;
-        if (fast) {
-          std::vector<double> pp;
-          pow2_twiddle_tables(L, roots.data(), &pp, &off2, &off3);
-          off2 += L;
-          off3 += L;
-          all.insert(all.end(), pp.begin(), pp.end());
-        }
-        std::vector<T> host(all.begin(), all.end());
-        void *dev = nullptr;
-        CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(T)));
-        CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-        pl->tables.push_back(dev);
-        it = table_of.emplace(2 * L + (fast ? 1 : 0), TableSet{dev, off2, off3, fast}).first;
-      }
-      const TableSet &ts = it->second;
-      sp.twiddle = ts.dev;
-      if (g.op == OP_R2R) {
-        const int M = 8 * sp.r2r_D;
-        auto jt = table_of.find(-M);
-        if (jt == table_of.end()) {
-          std::vector<double> roots(2 * (size_t)M);
-          make_twiddles_f64(M, roots.data());
-          std::vector<T> host(roots.begin(), roots.end());
-          void *dev = nullptr;
-          CUDA_OK(cudaMalloc(&dev, host.size() * sizeof(T)));
-          CUDA_OK(cudaMemcpy(dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
-          pl->tables.push_back(dev);
-          jt = table_of.emplace(-M, TableSet{dev, 0, 0, false}).first;
-        }
-        sp.tw_r2r = jt->second.dev;
-      }
-      if (fast) {
-        sp.tw2 = static_cast<const T *>(ts.dev) + 2 * ts.off2;
-        sp.tw3 = static_cast<const T *>(ts.dev) + 2 * ts.off3;
-        pow2_prepare<T>(g, sp);
-      }
-      if (g.ntile > 0 && !(fast && sp.fast)) {
-        *err = "internal: micro-blocked stage is not eligible for the register-resident kernel";
+      const int tl = fast ? pow2_pick_tile<T>(g, L) : generic_pick_tile<T>(g, L);
+      if (tl <= 0) {
+        *err = "transform length " + std::to_string(L) + " does not fit the shared-memory kernels";
         return false;
       }
+      stage_params_tiles(g, sp, tl);
+      sp.nfac = factorize_generic(L, sp.fac);
+      if (g.op != OP_COPY) {
+        auto it = table_of.find(2 * L + (fast ? 1 : 0));
+        if (it == table_of.end()) {
+          // unit roots in fp64 (< 1 ulp), then the layouts the kernels want, rounded once to T
+          std::vector<double> roots(2 * (size_t)L);
+          make_twiddles_f64(L, roots.data());
+          std::vector<double> all(roots);
+          size_t off2 = 0, off3 = 0;
+          if (fast) {
+            std::vector<double> pp;
+            pow2_twiddle_tables(L, roots.data(), &pp, &off2, &off3);
+            off2 += L;
+            off3 += L;
+            all.insert(all.end(), pp.begin(), pp.end());
+          }
+          std::vector<T> host(all.begin(), all.end());
+          void *dev = upload_device(host.data(), host.size() * sizeof(T), pl);
+          it = table_of.emplace(2 * L + (fast ? 1 : 0), TableSet{dev, off2, off3}).first;
+        }
+        const TableSet &ts = it->second;
+        sp.twiddle = ts.dev;
+        if (fast) {
+          sp.tw2 = static_cast<const T *>(ts.dev) + 2 * ts.off2;
+          sp.tw3 = static_cast<const T *>(ts.dev) + 2 * ts.off3;
+          pow2_prepare<T>(g, sp);
+        }
+      }
+    }
+    if (g.ntile > 0 && !(fast && sp.fast)) {
+      *err = "internal: micro-blocked stage is not eligible for the register-resident kernel";
+      return false;
     }
     pl->params.push_back(sp);
     pl->use_pow2.push_back(fast ? 1 : 0);
+    pl->kernel_kind.push_back(kind);
   }
   return true;
 }
@@ -472,6 +439,7 @@ void plan_destroy(PlanBase *pl) {
   if (pl->fuse.ring) cudaFree(pl->fuse.ring);
   if (pl->fuse.fp.done) cudaFree(pl->fuse.fp.done);
   for (void *t : pl->tables) cudaFree(t);
+  if (pl->mixed_ws) cudaFree(pl->mixed_ws);
   for (int k = 0; k < 3; k++)
     if (pl->scratch[k]) cudaFree(pl->scratch[k]);
   for (int t = 0; t < kMaxGroups; t++)
@@ -654,8 +622,13 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
     if (pl->stage_timing) cudaEventRecord(pl->events[2 * i], st);
     if (sp.ntiles > 0) {
       cudaError_t e;
-      if (pl->prec == PREC_F64) e = pl->use_pow2[i] ? launch_stage_pow2<double>(sp, st) : launch_stage_generic<double>(sp, st);
-      else e = pl->use_pow2[i] ? launch_stage_pow2<float>(sp, st) : launch_stage_generic<float>(sp, st);
+      const int kk = pl->kernel_kind[i];
+      if (pl->prec == PREC_F64)
+        e = kk == KERNEL_POW2 ? launch_stage_pow2<double>(sp, st)
+                              : (kk == KERNEL_MIXED ? launch_stage_mixed<double>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st) : launch_stage_generic<double>(sp, st));
+      else
+        e = kk == KERNEL_POW2 ? launch_stage_pow2<float>(sp, st)
+                              : (kk == KERNEL_MIXED ? launch_stage_mixed<float>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st) : launch_stage_generic<float>(sp, st));
       CUDA_OK(e);
     }
     if (pl->stage_timing) cudaEventRecord(pl->events[2 * i + 1], st);

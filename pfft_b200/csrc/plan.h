@@ -13,6 +13,7 @@ namespace pfb {
 
 enum Precision : int { PREC_F64 = 0, PREC_F32 = 1 };
 enum TransportKind : int { TR_AUTO = 0, TR_NCCL = 1, TR_P2P = 2 };
+enum KernelKind : int { KERNEL_GENERIC = 0, KERNEL_POW2 = 1, KERNEL_MIXED = 2 };
 
 // Same fields as the reference's timer (kernel/ipfft.h:208-219) so that
 // pfft_convert_timer2vec keeps its documented layout (kernel/timer.c:297-319).
@@ -65,6 +66,9 @@ struct PlanBase {
   int assign_key = -1;
   std::vector<StageParams> params;
   std::vector<int> use_pow2;
+  std::vector<int> kernel_kind;   // KernelKind per stage
+  void *mixed_ws = nullptr;       // global workspace of the any-length kernel (lines beyond shared memory)
+  size_t mixed_ws_bytes = 0;
   std::vector<void *> tables;     // device twiddle tables owned by the plan
   cudaStream_t stream = nullptr;
   int transport = TR_P2P;

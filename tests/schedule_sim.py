@@ -160,15 +160,20 @@ def rank_of(np_, coords):
     return r
 
 
-def simulate(scheds, user_in):
+def simulate(scheds, user_in, stage_fn=None):
     """scheds: list over ranks of schedule dicts; user_in: list over ranks of flat input arrays.
-    Returns list over ranks of flat output arrays (the user's out buffers)."""
+    Returns list over ranks of flat output arrays (the user's out buffers).
+    stage_fn(rank, stage index, stage dict, input buffer) -> list of output chunks replaces the numpy
+    interpretation of a stage (tests/test_kernel_emulation.py plugs in the emulated CUDA kernel body)."""
     P = len(scheds)
     nst = len(scheds[0]["stages"])
     assert all(len(s["stages"]) == nst for s in scheds)
     cur = list(user_in)
     for i in range(nst):
-        outs = [run_stage(scheds[r]["stages"][i], cur[r]) for r in range(P)]
+        if stage_fn is None:
+            outs = [run_stage(scheds[r]["stages"][i], cur[r]) for r in range(P)]
+        else:
+            outs = [stage_fn(r, i, scheds[r]["stages"][i], cur[r]) for r in range(P)]
         xi = scheds[0]["stages"][i]["exchange"]
         if xi < 0:
             cur = [np.concatenate(o) if len(o) > 1 else o[0] for o in outs]
