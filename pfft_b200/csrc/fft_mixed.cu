@@ -17,7 +17,7 @@ namespace pfb {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 256;      // per CTA when two CTAs share an SM; one resident CTA runs 2 * kThreads
 constexpr size_t kSmemMax = 227 * 1024;
 
 // radices with a codelet, largest first (the first pass needs no twiddles: give it the most work)
@@ -113,8 +113,8 @@ struct HostExec {
   }
 };
 
-template <typename T, bool GWS>
-__global__ void __launch_bounds__(kThreads) stage_mixed_kernel(const __grid_constant__ StageParams sp) {
+template <typename T, bool GWS, int MAXT, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) stage_mixed_kernel(const __grid_constant__ StageParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *buf = GWS ? reinterpret_cast<cx<T> *>(sp.mx.ws) + (size_t)blockIdx.x * (size_t)sp.mx.ws_stride
                    : reinterpret_cast<cx<T> *>(smem_raw);
@@ -206,7 +206,17 @@ bool mixed_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, 
   mx.dnout = make_fastdiv((unsigned)std::max(1, sp.nout));
   mx.diblk = make_fastdiv((unsigned)std::max(1, sp.iblk));
   mx.doblk = make_fastdiv((unsigned)std::max(1, sp.oblk));
+  mx.dnin2 = make_fastdiv((unsigned)std::max(1, sp.nin / 2));
+  mx.dnout2 = make_fastdiv((unsigned)std::max(1, sp.nout / 2));
   mx.dL = make_fastdiv((unsigned)std::max(1, mx.L));
+  // packed real lines whose rows are contiguous and start at even offsets move two reals per access
+  auto all_even = [&](bool in_side) {
+    for (int k = 0; k < g.nbatch; k++)
+      if ((in_side ? g.batch[k].istride : g.batch[k].ostride) % 2) return false;
+    return true;
+  };
+  mx.in_pairs = (mx.half_real == 1 && g.istride == 1 && g.iseg_stride == 0 && sp.nin % 2 == 0 && sp.zin % 2 == 0 && all_even(true)) ? 1 : 0;
+  mx.out_pairs = (mx.half_real == 2 && g.ostride == 1 && g.noseg == 1 && sp.nout % 2 == 0 && sp.zout % 2 == 0 && all_even(false)) ? 1 : 0;
   mx.dLc = make_fastdiv((unsigned)std::max(1, mx.Lc));
   // ---- tables
   std::vector<long double> re, im;
@@ -271,23 +281,37 @@ cudaError_t launch_stage_mixed(StageParams &sp, void **ws, size_t *ws_bytes, cud
     }
     sp.mx.ws = *ws;
     sp.mx.ws_stride = (long long)(tile_bytes / (2 * sizeof(T)));
-    stage_mixed_kernel<T, true><<<(unsigned)grid, kThreads, 0, stream>>>(sp);
+    stage_mixed_kernel<T, true, kThreads><<<(unsigned)grid, kThreads, 0, stream>>>(sp);
     launch_counter()++;
     return cudaGetLastError();
   }
-  auto kern = stage_mixed_kernel<T, false>;
+  // two resident CTAs of 256 threads need <= 128 registers per thread (the fp64 radix-13/16 butterflies then spill a
+  // little); PFFT_B200_MIXED_MINB=1 lifts the cap (one resident CTA with all the registers it wants)
+  static const int minb = [] {
+    const char *e = getenv("PFFT_B200_MIXED_MINB");
+    return e ? atoi(e) : 2;
+  }();
+  using K = void (*)(StageParams);
+  K kerns[3] = {stage_mixed_kernel<T, false, kThreads, 1>, stage_mixed_kernel<T, false, kThreads, 2>,
+                stage_mixed_kernel<T, false, 2 * kThreads, 1>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-    if (e != cudaSuccess) return e;
+    for (K k : kerns) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+      if (e != cudaSuccess) return e;
+    }
     attr_set = true;
   }
   if (tile_bytes > kSmemMax) return cudaErrorInvalidValue;
+  const bool two_fit = 2 * (tile_bytes + 1024) <= kSmemMax;
+  // one resident CTA: 512 threads keep 16 warps per SM (fp32 only: the fp64 butterflies need more than 128 registers)
+  const int which = (two_fit && minb >= 2) ? 1 : ((!two_fit && sizeof(T) == 4) ? 2 : 0);
+  const int threads = which == 2 ? 2 * kThreads : kThreads;
   int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, tile_bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kerns[which], threads, tile_bytes);
   if (per_sm < 1) per_sm = 1;
   const long long grid = std::min<long long>(sp.ntiles, (long long)sms * per_sm);
-  kern<<<(unsigned)grid, kThreads, tile_bytes, stream>>>(sp);
+  kerns[which]<<<(unsigned)grid, threads, tile_bytes, stream>>>(sp);
   launch_counter()++;
   return cudaGetLastError();
 }

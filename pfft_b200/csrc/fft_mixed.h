@@ -144,46 +144,75 @@ PFB_HD void mixed_tile(const StageParams &sp, cx<T> *buf, long long ibase, long 
     });
   }
 
-  // ---- 1. load
+  // ---- 1. load: kLoadBatch independent global loads in flight per thread, then the shared-memory writes
   ex.run([&](int tid, int nthr) {
+    constexpr int U = 8;
     const bool contiguous = sp.istride == 1;
-    const unsigned total = (unsigned)(contiguous ? tvalid : tl) * (unsigned)sp.nin;
+    const bool pairs = mx.in_pairs != 0;       // packed r2c line, contiguous and aligned: two reals per load
+    const int count = pairs ? sp.nin >> 1 : sp.nin;
+    const FastDiv &dcount = pairs ? mx.dnin2 : mx.dnin;
+    const unsigned total = (unsigned)(contiguous ? tvalid : tl) * (unsigned)count;
     const bool seg_in = sp.iseg_stride != 0;
-    for (unsigned e = (unsigned)tid; e < total; e += (unsigned)nthr) {
-      const MxItem it = mx_item(e, contiguous, mx.dnin, sp.nin, mx.tl_shift, tvalid);
-      if (!it.ok) continue;
-      const int j = it.j, tt = it.tt;
-      long long off = ibase + (long long)tt * t_is;
-      if (seg_in) {
-        const int seg = (int)fd_div((unsigned)j, mx.diblk);
-        off += (long long)seg * sp.iseg_stride + (long long)(j - seg * sp.iblk) * sp.istride;
-      } else {
-        off += (long long)j * sp.istride;
-      }
-      const int p = j + sp.zin;          // position inside the zero-padded line
-      if (sp.in_real) {
-        T xr = reinterpret_cast<const T *>(sp.in)[off];
-        if (sp.mod_in.on && mx_sign_mod(sp.mod_in, j) < 0) xr = -xr;
-        if (half == 1) {
-          // two consecutive reals = one complex point
-          reinterpret_cast<T *>(B0 + (size_t)tt * pitch + mx_phys(p >> 1))[p & 1] = xr;
-        } else if (sp.op == OP_R2R) {
-          // w_j x_j exp(-i pi b jj / D), jj = position inside the logical line of n reals
-          if ((p == 0 && sp.r2r_half0) || (p == sp.n - 1 && sp.r2r_halfn)) xr *= (T)0.5;
-          const cx<T> w = mx_ldg(reinterpret_cast<const cx<T> *>(sp.tw_r2r) + (int)(((long long)2 * sp.r2r_b2 * p) % (8ll * sp.r2r_D)));
-          B0[(size_t)tt * pitch + mx_phys(p)] = cx<T>{xr * w.x, xr * w.y};
+    for (unsigned e0 = (unsigned)tid; e0 < total; e0 += (unsigned)nthr * U) {
+      MxItem it[U];
+      cx<T> val[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned e = e0 + (unsigned)u * (unsigned)nthr;
+        it[u].ok = false;
+        if (e >= total) continue;
+        it[u] = mx_item(e, contiguous, dcount, count, mx.tl_shift, tvalid);
+        if (!it[u].ok) continue;
+        const int j = it[u].j;
+        long long off = ibase + (long long)it[u].tt * t_is;
+        if (seg_in) {
+          const int seg = (int)fd_div((unsigned)j, mx.diblk);
+          off += (long long)seg * sp.iseg_stride + (long long)(j - seg * sp.iblk) * sp.istride;
         } else {
-          B0[(size_t)tt * pitch + mx_phys(p)] = swap_in ? cx<T>{(T)0, xr} : cx<T>{xr, (T)0};
+          off += (long long)j * sp.istride;
         }
-      } else {
-        cx<T> v = reinterpret_cast<const cx<T> *>(sp.in)[off];
-        if (sp.conj_in) v.y = -v.y;
-        if (sp.mod_in.on && mx_sign_mod(sp.mod_in, j) < 0) { v.x = -v.x; v.y = -v.y; }
-        if (half == 2) {
-          B1[(size_t)tt * pitch + p] = v;      // Hermitian half spectrum X[0..M], unpadded indexing
+        if (pairs) val[u] = reinterpret_cast<const cx<T> *>(sp.in)[((off - j) >> 1) + j];   // line base counts reals (even)
+        else if (sp.in_real) val[u].x = reinterpret_cast<const T *>(sp.in)[off];
+        else val[u] = reinterpret_cast<const cx<T> *>(sp.in)[off];
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        if (!it[u].ok) continue;
+        const int j = it[u].j, tt = it[u].tt;
+        if (pairs) {
+          cx<T> v = val[u];
+          if (sp.mod_in.on) {
+            if (mx_sign_mod(sp.mod_in, 2 * j) < 0) v.x = -v.x;
+            if (mx_sign_mod(sp.mod_in, 2 * j + 1) < 0) v.y = -v.y;
+          }
+          B0[(size_t)tt * pitch + mx_phys(j + (sp.zin >> 1))] = v;
+          continue;
+        }
+        const int p = j + sp.zin;          // position inside the zero-padded line
+        if (sp.in_real) {
+          T xr = val[u].x;
+          if (sp.mod_in.on && mx_sign_mod(sp.mod_in, j) < 0) xr = -xr;
+          if (half == 1) {
+            // two consecutive reals = one complex point
+            reinterpret_cast<T *>(B0 + (size_t)tt * pitch + mx_phys(p >> 1))[p & 1] = xr;
+          } else if (sp.op == OP_R2R) {
+            // w_j x_j exp(-i pi b jj / D), jj = position inside the logical line of n reals
+            if ((p == 0 && sp.r2r_half0) || (p == sp.n - 1 && sp.r2r_halfn)) xr *= (T)0.5;
+            const cx<T> w = mx_ldg(reinterpret_cast<const cx<T> *>(sp.tw_r2r) + (int)(((long long)2 * sp.r2r_b2 * p) % (8ll * sp.r2r_D)));
+            B0[(size_t)tt * pitch + mx_phys(p)] = cx<T>{xr * w.x, xr * w.y};
+          } else {
+            B0[(size_t)tt * pitch + mx_phys(p)] = swap_in ? cx<T>{(T)0, xr} : cx<T>{xr, (T)0};
+          }
         } else {
-          if (swap_in) { const T t = v.x; v.x = v.y; v.y = t; }
-          B0[(size_t)tt * pitch + mx_phys(p)] = v;
+          cx<T> v = val[u];
+          if (sp.conj_in) v.y = -v.y;
+          if (sp.mod_in.on && mx_sign_mod(sp.mod_in, j) < 0) { v.x = -v.x; v.y = -v.y; }
+          if (half == 2) {
+            B1[(size_t)tt * pitch + p] = v;      // Hermitian half spectrum X[0..M], unpadded indexing
+          } else {
+            if (swap_in) { const T t = v.x; v.x = v.y; v.y = t; }
+            B0[(size_t)tt * pitch + mx_phys(p)] = v;
+          }
         }
       }
     }
@@ -281,8 +310,26 @@ PFB_HD void mixed_tile(const StageParams &sp, cx<T> *buf, long long ibase, long 
   // ---- 3. store the kept outputs
   ex.run([&](int tid, int nthr) {
     const bool contiguous = sp.ostride == 1;
-    const unsigned total = (unsigned)(contiguous ? tvalid : tl) * (unsigned)sp.nout;
     const bool seg_out = sp.noseg > 1;
+    if (mx.out_pairs) {
+      // packed c2r line, contiguous and aligned: one 2-real store per packed point
+      const int count = sp.nout >> 1;
+      const unsigned total = (unsigned)tvalid * (unsigned)count;
+      for (unsigned e = (unsigned)tid; e < total; e += (unsigned)nthr) {
+        const int tt = (int)fd_div(e, mx.dnout2);
+        const int c = (int)(e - (unsigned)tt * (unsigned)count);
+        const cx<T> r = S[(size_t)tt * pitch + mx_phys(c + (sp.zout >> 1))];
+        cx<T> v{r.y, r.x};
+        if (sp.mod_out.on) {
+          if (mx_sign_mod(sp.mod_out, 2 * c) < 0) v.x = -v.x;
+          if (mx_sign_mod(sp.mod_out, 2 * c + 1) < 0) v.y = -v.y;
+        }
+        const long long off = obase + (long long)tt * t_os;       // reals; even by construction
+        reinterpret_cast<cx<T> *>(sp.out[0])[(off >> 1) + c] = v;
+      }
+      return;
+    }
+    const unsigned total = (unsigned)(contiguous ? tvalid : tl) * (unsigned)sp.nout;
     for (unsigned e = (unsigned)tid; e < total; e += (unsigned)nthr) {
       const MxItem it = mx_item(e, contiguous, mx.dnout, sp.nout, mx.tl_shift, tvalid);
       if (!it.ok) continue;

@@ -41,12 +41,13 @@ struct MixedParams {
   int Lc;                    // length of the transforms actually run: L, or the Bluestein length M >= 2L - 1
   int half_real;             // 0: complex line, 1: r2c on n/2 packed points, 2: c2r on n/2 packed points
   int bluestein, swap, zero_fill;
+  int in_pairs, out_pairs;   // packed real lines moved two reals at a time (contiguous, even offsets)
   int pitch;                 // complex elements per buffer line (padded)
   int tl_shift;              // log2(tl)
   int gws;                   // buffers live in the global workspace (line does not fit shared memory)
   int npass;
   MixedPass pass[kMaxMixedPass];
-  FastDiv dnin, dnout, diblk, doblk, dL, dLc;
+  FastDiv dnin, dnout, diblk, doblk, dL, dLc, dnin2, dnout2;
   const void *tw;            // Lc entries exp(-2 pi i k / Lc)
   const void *tw_half;       // n/2 + 1 entries exp(-2 pi i k / n) (packed real lines)
   const void *chirp;         // Bluestein: L entries exp(-i pi j^2 / L)

@@ -459,6 +459,61 @@ static bool device_accessible(const void *p) {
   return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
+// ---- host-pointer executes ---------------------------------------------------------------------
+// Arrays the device cannot address (plain or pinned host memory) are staged through two process-wide
+// device areas.  The copies run on two copy streams of their own, in chunks, so that consecutive
+// executes keep BOTH PCIe directions busy: the device-to-host copy of one transform's output overlaps the
+// host-to-device copy of the next transform's input (a 3-D FFT needs all of its input before any output
+// is final, so inside ONE transform the two copies cannot overlap).  Ordering:
+//   * read-after-write through host memory: every D2H chunk records an event; an H2D chunk whose host
+//     range overlaps a pending D2H waits for the covering chunk's event -- backward(forward(x)) streams;
+//   * the input staging area is reused: H2D waits for the previous staged transform's last kernel;
+//   * the output staging area is reused: a staged transform's kernels wait for the previous D2H.
+// pfft_execute then synchronises (the reference call blocks); pfftb200_execute_async does not.
+namespace {
+constexpr size_t kCopyChunk = (size_t)128 << 20;
+struct HostPending {
+  const char *base;
+  size_t bytes;
+  std::vector<cudaEvent_t> done;   // one per kCopyChunk
+};
+std::vector<HostPending> g_pending;
+std::vector<cudaEvent_t> g_event_pool;
+cudaStream_t g_h2d = nullptr, g_d2h = nullptr;
+cudaEvent_t g_compute_done = nullptr, g_d2h_done = nullptr;
+bool g_have_compute_done = false, g_have_d2h_done = false;
+
+cudaEvent_t take_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return e;
+}
+void copy_streams() {
+  if (g_h2d) return;
+  CUDA_OK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&g_d2h, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&g_compute_done, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&g_d2h_done, cudaEventDisableTiming));
+}
+// forget device-to-host copies that have landed
+void purge_pending() {
+  for (size_t i = 0; i < g_pending.size();) {
+    if (cudaEventQuery(g_pending[i].done.back()) == cudaSuccess) {
+      for (cudaEvent_t e : g_pending[i].done) g_event_pool.push_back(e);
+      g_pending.erase(g_pending.begin() + i);
+    } else {
+      cudaGetLastError();
+      i++;
+    }
+  }
+}
+}  // namespace
+
 // Process-wide staging areas for host-pointer executes (0: input, 1: output); grow only.
 static void *staging_area(int which, size_t bytes, cudaStream_t st) {
   static void *area[2] = {nullptr, nullptr};
@@ -471,6 +526,45 @@ static void *staging_area(int which, size_t bytes, cudaStream_t st) {
     cap[which] = bytes;
   }
   return area[which];
+}
+
+static void staged_h2d(void *dev, const void *host, size_t bytes, cudaStream_t st) {
+  copy_streams();
+  purge_pending();
+  if (g_have_compute_done) CUDA_OK(cudaStreamWaitEvent(g_h2d, g_compute_done, 0));
+  const char *h = static_cast<const char *>(host);
+  for (size_t off = 0; off < bytes; off += kCopyChunk) {
+    const size_t len = std::min(kCopyChunk, bytes - off);
+    for (const HostPending &p : g_pending) {
+      if (h + off + len <= p.base || p.base + p.bytes <= h + off) continue;
+      // the D2H stream runs its chunks in order: waiting for the last overlapping one covers them all
+      const size_t last_byte = std::min<size_t>((size_t)(h + off + len - p.base), p.bytes) - 1;
+      CUDA_OK(cudaStreamWaitEvent(g_h2d, p.done[last_byte / kCopyChunk], 0));
+    }
+    CUDA_OK(cudaMemcpyAsync(static_cast<char *>(dev) + off, h + off, len, cudaMemcpyHostToDevice, g_h2d));
+  }
+  cudaEvent_t landed = take_event();
+  CUDA_OK(cudaEventRecord(landed, g_h2d));
+  CUDA_OK(cudaStreamWaitEvent(st, landed, 0));
+  g_event_pool.push_back(landed);      // (a recorded event may be re-recorded once its waits are enqueued)
+}
+
+static void staged_d2h(void *host, const void *dev, size_t bytes) {
+  CUDA_OK(cudaStreamWaitEvent(g_d2h, g_compute_done, 0));   // (recorded by the caller behind the last kernel)
+  HostPending p;
+  p.base = static_cast<const char *>(host);
+  p.bytes = bytes;
+  for (size_t off = 0; off < bytes; off += kCopyChunk) {
+    const size_t len = std::min(kCopyChunk, bytes - off);
+    CUDA_OK(cudaMemcpyAsync(static_cast<char *>(host) + off, static_cast<const char *>(dev) + off, len, cudaMemcpyDeviceToHost, g_d2h));
+    cudaEvent_t e = take_event();
+    CUDA_OK(cudaEventRecord(e, g_d2h));
+    p.done.push_back(e);
+  }
+  if (p.done.empty()) return;
+  CUDA_OK(cudaEventRecord(g_d2h_done, g_d2h));
+  g_have_d2h_done = true;
+  g_pending.push_back(p);
 }
 
 // Choose, for every boundary between two stages, the buffer that holds it.  A stage never
@@ -559,11 +653,12 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
   bool copy_back = false, staged_in = false;
   if (pl->user_in_bytes && !device_accessible(in)) {
     dev_in = staging_area(0, pl->user_in_bytes, st);
-    CUDA_OK(cudaMemcpyAsync(dev_in, in, pl->user_in_bytes, cudaMemcpyHostToDevice, st));
+    staged_h2d(dev_in, in, pl->user_in_bytes, st);
     staged_in = true;
   }
   if (pl->user_out_bytes && !device_accessible(out)) {
     dev_out = staging_area(1, pl->user_out_bytes, st);
+    if (g_have_d2h_done) CUDA_OK(cudaStreamWaitEvent(st, g_d2h_done, 0));   // the area may still be on its way to the host
     copy_back = true;
   }
   const size_t nst = s.stages.size();
@@ -638,9 +733,16 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
       xch_host[g.exchange % 16] += MPI_Wtime() - t0;
     }
   }
-  if (copy_back) CUDA_OK(cudaMemcpyAsync(out, dev_out, pl->user_out_bytes, cudaMemcpyDeviceToHost, st));
+  if (staged_in || copy_back) {
+    // the staging areas are free for the next host-pointer execute once these kernels are done
+    copy_streams();
+    CUDA_OK(cudaEventRecord(g_compute_done, st));
+    g_have_compute_done = true;
+  }
+  if (copy_back) staged_d2h(out, dev_out, pl->user_out_bytes);
   if (blocking) {
     CUDA_OK(cudaStreamSynchronize(st));
+    if (copy_back) CUDA_OK(cudaStreamSynchronize(g_d2h));
     if (pl->stage_timing) {
       TimerData &tm = pl->timer;
       tm.iter++;
