@@ -128,6 +128,9 @@ struct Stage {
   int in_buf = 0, out_buf = 0;   // buffer ids, see BufId
   int exchange = -1;          // index into Schedule::exchanges applied to this stage's output, or -1
   INT in_elems = 0, out_elems = 0;   // footprint in elements (for buffer sizing / roofline bytes)
+  // where the stage's time is booked in the reference's timer layout (kernel/timer.c:297-319):
+  // >= 0: trafo[slot]; -1 / -2: remap_3dto2d[0] / [1] (stages of the 3-D-mesh remap)
+  int timer_slot = 0;
 };
 
 enum BufId : int { BUF_USER_IN = 0, BUF_USER_OUT = 1, BUF_A = 2, BUF_B = 3, BUF_RING = 4 };

@@ -20,7 +20,7 @@ namespace {
 constexpr int kThreads = 256;      // per CTA when two CTAs share an SM; one resident CTA runs 2 * kThreads
 constexpr size_t kSmemMax = 227 * 1024;
 
-// radices with a codelet, largest first (the first pass needs no twiddles: give it the most work)
+// radices with a codelet, large ones first (the first pass needs no twiddles: give it the most work)
 bool radix_schedule(int L, std::vector<int> *out) {
   out->clear();
   int m = L;
@@ -41,6 +41,12 @@ bool radix_schedule(int L, std::vector<int> *out) {
   if (m != 1) return false;
   std::sort(f.begin(), f.end(), [](int a, int b) { return a > b; });
   if ((int)f.size() > kMaxMixedPass) return false;
+  // The first pass touches positions R i + r (stride-R butterflies): conflict-free in shared memory for radix 16
+  // (17-element padded pitch) and for odd radices, 2- to 4-way conflicts for 2, 4, 8 -- so a 16 goes first if there
+  // is one, else the largest odd radix; later passes have strides that are multiples of 16 or odd.
+  auto lead = std::find(f.begin(), f.end(), 16);
+  if (lead == f.end()) lead = std::find_if(f.begin(), f.end(), [](int r) { return r % 2 == 1; });
+  if (lead != f.end() && lead != f.begin()) std::rotate(f.begin(), lead, lead + 1);
   *out = f;
   return true;
 }
@@ -173,19 +179,23 @@ bool mixed_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, 
     p.dNs = make_fastdiv((unsigned)p.Ns);
     Ns *= p.R;
   }
-  // buffer line: padded transform length; the c2r spectrum line needs L + 1 unpadded entries as well
+  // buffer line: padded transform length
   mx.pitch = mx.Lc + (mx.Lc >> 4) + 2;
   // what the load leaves untouched must be cleared: zero padding of pruned inputs, the Bluestein tail, DCT/DST padding
   const int line_in = mx.half_real == 2 ? n / 2 + 1 : (mx.half_real == 1 ? n : (g.op == OP_C2R ? n / 2 + 1 : n));
   mx.zero_fill = (sp.nin != line_in || sp.zin != 0 || mx.bluestein || g.op == OP_R2R) ? 1 : 0;
   // ---- tile: lines per CTA (a power of two) against the shared-memory budget
-  const size_t per_line = 2 * (size_t)mx.pitch * csize;
+  const size_t per_line = (size_t)mx.pitch * csize;
   const bool strided = g.istride != 1 || g.ostride != 1;
   const int want = strided ? (int)std::max<size_t>(1, 128 / csize) : 1;   // 128-byte runs on a strided side
   const long long fit1 = (long long)((kSmemMax - 1024) / per_line), fit2 = (long long)((kSmemMax / 2 - 1024) / per_line);
   int tl;
   mx.gws = 0;
-  if (fit2 >= want) tl = std::min(floor_pow2(fit2), std::max(want, 4));   // two resident CTAs overlap each other's phases
+  // two resident CTAs overlap each other's phases; short lines get more of them per tile (>= 4096 points) so that
+  // the per-phase barriers are amortised
+  int amort = 1;
+  while (amort * mx.Lc < 4096 && amort < 64) amort *= 2;
+  if (fit2 >= want) tl = std::min(floor_pow2(fit2), std::max(std::max(want, 4), amort));
   else if (fit1 >= 1) tl = std::min(floor_pow2(fit1), want);
   else { tl = 1; mx.gws = 1; }
   static const int forced = [] {
@@ -219,6 +229,20 @@ bool mixed_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, 
   mx.out_pairs = (mx.half_real == 2 && g.ostride == 1 && g.noseg == 1 && sp.nout % 2 == 0 && sp.zout % 2 == 0 && all_even(false)) ? 1 : 0;
   mx.dLc = make_fastdiv((unsigned)std::max(1, mx.Lc));
   // ---- tables
+  if (mx.npass > 1) {
+    // digit reversal for the in-place decimation-in-time passes: n = r_P + R_P (r_{P-1} + R_{P-1} (...)) sits at
+    // sum_p r_p Ns_p (Ns_p = product of the radices of the passes before p)
+    std::vector<int> rev(mx.Lc);
+    for (int i = 0; i < mx.Lc; i++) {
+      int m = i, pos = 0;
+      for (int q = mx.npass - 1; q >= 0; q--) {
+        pos += (m % mx.pass[q].R) * mx.pass[q].Ns;
+        m /= mx.pass[q].R;
+      }
+      rev[i] = pos;
+    }
+    mx.rev = static_cast<const int *>(upload(rev.data(), rev.size() * sizeof(int), ctx));
+  }
   std::vector<long double> re, im;
   if (mx.npass > 0) {
     unit_roots_ld(mx.Lc, &re, &im);
@@ -259,7 +283,7 @@ bool mixed_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, 
 template <typename T>
 cudaError_t launch_stage_mixed(StageParams &sp, void **ws, size_t *ws_bytes, cudaStream_t stream) {
   if (sp.ntiles <= 0) return cudaSuccess;
-  const size_t tile_bytes = 2 * (size_t)sp.tl * sp.mx.pitch * 2 * sizeof(T);
+  const size_t tile_bytes = (size_t)sp.tl * sp.mx.pitch * 2 * sizeof(T);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -320,7 +344,7 @@ cudaError_t launch_stage_mixed(StageParams &sp, void **ws, size_t *ws_bytes, cud
 template <typename T>
 void emulate_stage_mixed(StageParams &sp) {
   if (sp.ntiles <= 0) return;
-  std::vector<cx<T>> buf(2 * (size_t)sp.tl * sp.mx.pitch);
+  std::vector<cx<T>> buf((size_t)sp.tl * sp.mx.pitch);
   HostExec ex{kThreads};
   for (long long tile = 0; tile < sp.ntiles; tile++) {
     long long ibase, obase, t_is, t_os;

@@ -48,6 +48,7 @@ struct MixedParams {
   int npass;
   MixedPass pass[kMaxMixedPass];
   FastDiv dnin, dnout, diblk, doblk, dL, dLc, dnin2, dnout2;
+  const int *rev;            // Lc entries: natural index -> digit-reversed position (null: identity)
   const void *tw;            // Lc entries exp(-2 pi i k / Lc)
   const void *tw_half;       // n/2 + 1 entries exp(-2 pi i k / n) (packed real lines)
   const void *chirp;         // Bluestein: L entries exp(-i pi j^2 / L)

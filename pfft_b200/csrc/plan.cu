@@ -753,11 +753,19 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
         float ms = 0;
         cudaEventElapsedTime(&ms, pl->events[2 * i], pl->events[2 * i + 1]);
         pl->last_stage_ms[i] = ms;
-        tm.trafo[std::min<size_t>(i, tm.trafo.size() - 1)] += ms * 1e-3;
+        // the reference's slots (kernel/timer.c:297-319): trafo[] per transform stage, remap_3dto2d[] for the
+        // stages of the 3-D mesh remap; itwiddle / otwiddle stay 0 (the modulations are fused into the stages)
+        const int slot = s.stages[i].timer_slot;
+        if (slot >= 0) tm.trafo[std::min<size_t>((size_t)slot, tm.trafo.size() - 1)] += ms * 1e-3;
+        else tm.remap_3dto2d[slot == -1 ? 0 : 1] += ms * 1e-3;
       }
-      for (size_t x = 0; x < s.exchanges.size(); x++) {
+      size_t xslot = 0;
+      for (size_t i = 0; i < nst; i++) {
+        const int x = s.stages[i].exchange;
+        if (x < 0 || (size_t)x >= s.exchanges.size()) continue;
         pl->last_xch_ms[x] = xch_host[x % 16] * 1e3;
-        if (!tm.remap.empty()) tm.remap[std::min<size_t>(x, tm.remap.size() - 1)] += xch_host[x % 16];
+        if (s.stages[i].timer_slot < 0) tm.remap_3dto2d[s.stages[i].timer_slot == -1 ? 0 : 1] += xch_host[x % 16];
+        else if (!tm.remap.empty()) tm.remap[std::min<size_t>(xslot++, tm.remap.size() - 1)] += xch_host[x % 16];
       }
     }
   }

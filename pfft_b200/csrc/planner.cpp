@@ -76,6 +76,7 @@ struct Step {
   int xch_mesh = -1;      // exchange after this step over this mesh dim
   int xch_split = -1, xch_gather = -1;
   INT split_blk = 0, split_n = 0, gather_blk = 0, gather_n = 0;
+  int remap3d = 0;        // 1 / 2: stage of the 3-D mesh remap in front of / behind the pencil schedule
 };
 
 struct Builder {
@@ -631,6 +632,7 @@ struct Builder {
         a.split_blk = ob1; a.split_n = l1; a.gather_blk = ib2; a.gather_n = block_extent(nn[2], mb2, c[GQ0]);
         cst.xch_mesh = GQ0; cst.xch_split = 0; cst.xch_gather = 2;
         cst.split_blk = ob0; cst.split_n = l0; cst.gather_blk = mb2; cst.gather_n = nn[2];
+        a.remap3d = b.remap3d = cst.remap3d = 1;
         steps.insert(steps.begin(), {a, b, cst});
       }
       if (ti.active) {
@@ -649,6 +651,7 @@ struct Builder {
         Step b{0, false, 1}, cst{2, false, 1}, e{1, false, 1};
         cst.xch_mesh = GQ1; cst.xch_split = 2; cst.xch_gather = 1;
         cst.split_blk = ib2; cst.split_n = block_extent(nn[2], mb2, c[GQ0]); cst.gather_blk = ob1; cst.gather_n = l1;
+        b.remap3d = cst.remap3d = e.remap3d = 2;
         steps.push_back(b);
         steps.push_back(cst);
         steps.push_back(e);
@@ -668,6 +671,7 @@ struct Builder {
     bool cur_real = cur.real;
     const Layout Lfinal = user_layout(false);
 
+    int trafo_slot = 0;
     for (size_t i = 0; i < steps.size(); i++) {
       const Step &st = steps[i];
       const HalfSizes &h = hs[st.half];
@@ -783,6 +787,7 @@ struct Builder {
       emit(st, Lin, Lout, h, first, last, noseg, seg_rows, mbk ? tilef[i] : nullptr);
       if (!s.error.empty()) return false;
       Stage &g = s.stages.back();
+      g.timer_slot = st.remap3d ? -st.remap3d : trafo_slot++;
 
       if (st.xch_mesh >= 0 && !last) {
         const int m = st.xch_mesh;
@@ -913,7 +918,7 @@ std::string schedule_to_json(const Schedule &s) {
       << "," << g.mod_in.start << "," << g.mod_in.half << "," << g.mod_in.extra << "],\"mod_out\":[" << g.mod_out.on
       << "," << g.mod_out.start << "," << g.mod_out.half << "," << g.mod_out.extra << "],\"in_buf\":" << g.in_buf
       << ",\"out_buf\":" << g.out_buf << ",\"exchange\":" << g.exchange << ",\"in_elems\":" << g.in_elems
-      << ",\"out_elems\":" << g.out_elems << "}";
+      << ",\"out_elems\":" << g.out_elems << ",\"timer_slot\":" << g.timer_slot << "}";
   }
   o << "],\"exchanges\":[";
   for (size_t i = 0; i < s.exchanges.size(); i++) {
