@@ -169,6 +169,26 @@ def reference_arm(args, cfg, config):
     return 0
 
 
+def nvlink_counters(index):
+    """(tx, rx) bytes moved over all NVLink links of GPU `index` since boot (nvidia-smi nvlink -gt d), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for l in out.splitlines():
+            l = l.strip()
+            if "Data Tx" in l or "Data Rx" in l:
+                kib = int(l.split(":")[-1].strip().split()[0])
+                seen = True
+                if "Tx" in l:
+                    tx += kib * 1024
+                else:
+                    rx += kib * 1024
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     def __init__(self, index):
         self.index = index
@@ -478,6 +498,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_ms_f, stage_ms_b = [], []
     barrier()
+    nvl0 = nvlink_counters(local_rank) if (world > 1 and rank == 0) else None
     with ClockSampler(local_rank) as clk:
         ev0.record()
         for i in range(args.steps):
@@ -490,6 +511,7 @@ def main():
         ev1.record()
         barrier()
     ms = ev0.elapsed_time(ev1)
+    nvl1 = nvlink_counters(local_rank) if nvl0 else None
     launches = pf.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -560,6 +582,12 @@ def main():
     t_hbm = hbm_bytes / (peak * 1e9) * 1e3
     combined = {"hbm_bytes_per_gpu": hbm_bytes, "nvlink_bytes_per_gpu": nvl_bytes, "hbm_peak_gbs": peak,
                 "t_hbm_ms": t_hbm, "t_measured_ms": t_tr, "nvlink_gbs_in_exchange_stages": nvl_rates or None}
+    if nvl0 and nvl1:
+        # hardware counters of rank 0's GPU around the timed loop (forward + backward per step move 2 x nvl_bytes each way)
+        combined["nvlink_counters_rank0"] = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / args.steps,
+                                             "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / args.steps,
+                                             "algorithmic_bytes_per_step_each_way": 2 * nvl_bytes,
+                                             "source": "nvidia-smi nvlink -gt d, all links of GPU %d" % local_rank}
     for tag, pk in (("measured", NVLINK_MEASURED), ("nominal", NVLINK_NOMINAL)):
         t_nvl = nvl_bytes / (pk * 1e9) * 1e3
         combined[tag] = {"nvlink_peak_gbs": pk, "t_nvlink_ms": t_nvl, "t_roof_serial_ms": t_hbm + t_nvl,

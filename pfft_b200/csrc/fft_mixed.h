@@ -223,16 +223,16 @@ PFB_HD void mixed_tile(const StageParams &sp, cx<T> *buf, long long ibase, long 
       return off;
     };
     for (unsigned e0 = (unsigned)tid; e0 < total; e0 += (unsigned)nthr * U) {
-      MxItem it[U];
       cx<T> val[U], val2[U];
+      unsigned okmask = 0;
 #pragma unroll
       for (int u = 0; u < U; u++) {
         const unsigned e = e0 + (unsigned)u * (unsigned)nthr;
-        it[u].ok = false;
         if (e >= total) continue;
-        it[u] = mx_item(e, contiguous, dcount, count, mx.tl_shift, tvalid);
-        if (!it[u].ok) continue;
-        const int j = it[u].j, tt = it[u].tt;
+        const MxItem it = mx_item(e, contiguous, dcount, count, mx.tl_shift, tvalid);
+        if (!it.ok) continue;
+        okmask |= 1u << u;
+        const int j = it.j, tt = it.tt;
         if (half == 2) {
           // spectrum entries at positions k and M - k of the zero-padded half spectrum (element j sits at j + zin)
           const int ja = j - sp.zin, jb = M - j - sp.zin;
@@ -250,8 +250,10 @@ PFB_HD void mixed_tile(const StageParams &sp, cx<T> *buf, long long ibase, long 
       }
 #pragma unroll
       for (int u = 0; u < U; u++) {
-        if (!it[u].ok) continue;
-        const int j = it[u].j, tt = it[u].tt;
+        if (!((okmask >> u) & 1)) continue;
+        // (the item is recomputed rather than kept: an array of structs would live in local memory)
+        const MxItem it = mx_item(e0 + (unsigned)u * (unsigned)nthr, contiguous, dcount, count, mx.tl_shift, tvalid);
+        const int j = it.j, tt = it.tt;
         cx<T> *line = B0 + (size_t)tt * pitch;
         if (half == 2) {
           // c2r, n = 2M: x[2j] + i x[2j+1] = sum_k Zf[k] exp(+2 pi i j k / M) with

@@ -15,7 +15,14 @@
 // all copies of each owned element (reduce): no packing, no per-dimension rounds, no
 // diagonal messages.  Source lookups are driven by small per-dimension tables built on
 // the host, so the kernels contain no integer division by run-time block sizes.
+//
+// Cost model: the call is in place and the array changes its shape (row pitch and plane pitch grow by the
+// halo widths), so every interior element moves as well -- one read + one write of the local block is the
+// floor for the re-layout, on top of the halo bytes that cross NVLink.  The implementation publishes the
+// block with one device-to-device copy (peers read their halos from it, this rank reads its interior from
+// it) and writes the new shape with one row-wise kernel: 2 reads + 2 writes of the block.
 #include <cuda_runtime.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <vector>
@@ -50,48 +57,59 @@ struct GcDev {
   int tuple;
 };
 
-template <typename T>
-__global__ void gc_gather_kernel(GcDev d, T *__restrict__ out) {
-  const long long total = (long long)d.ngc[0] * d.ngc[1] * d.ngc[2];
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const int i2 = (int)(p % d.ngc[2]);
-    const long long q = p / d.ngc[2];
-    const int i1 = (int)(q % d.ngc[1]);
-    const int i0 = (int)(q / d.ngc[1]);
-    const int c0 = d.own_c[0][i0], c1 = d.own_c[1][i1], c2 = d.own_c[2][i2];
-    const int l0 = d.own_l[0][i0], l1 = d.own_l[1][i1], l2 = d.own_l[2][i2];
-    const int rank = (c0 * d.np[1] + c1) * d.np[2] + c2;
-    const T *src = static_cast<const T *>(d.peer[rank]) +
-                   (((long long)l0 * d.ext[1][c1] + l1) * d.ext[2][c2] + l2) * d.tuple;
-    T *dst = out + p * d.tuple;
-    for (int h = 0; h < d.tuple; h++) dst[h] = src[h];
+// Both kernels walk ROWS of the last dimension: the owner / copy lookups of dimensions 0 and 1 are done once per
+// row, the threads of a CTA run along the row (coalesced accesses, whole grid points of `tuple` reals as one vector
+// when tuple is 1 or 2), and no thread executes an integer division per element.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) gc_gather_kernel(GcDev d, T *__restrict__ out) {
+  struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  const int rows = d.ngc[0] * d.ngc[1];
+  const int per_point = d.tuple / VEC;               // vectors per grid point
+  const int row_vecs = d.ngc[2] * per_point;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int i0 = row / d.ngc[1], i1 = row - i0 * d.ngc[1];
+    const int c0 = d.own_c[0][i0], c1 = d.own_c[1][i1];
+    const long long l01 = (long long)d.own_l[0][i0] * d.ext[1][c1] + d.own_l[1][i1];
+    const int rank01 = (c0 * d.np[1] + c1) * d.np[2];
+    V *dst = reinterpret_cast<V *>(out) + (long long)row * row_vecs;
+    for (int x = threadIdx.x; x < row_vecs; x += blockDim.x) {
+      const int i2 = per_point == 1 ? x : x / per_point, h = per_point == 1 ? 0 : x - i2 * per_point;
+      const int c2 = d.own_c[2][i2];
+      const V *src = reinterpret_cast<const V *>(d.peer[rank01 + c2]) + (l01 * d.ext[2][c2] + d.own_l[2][i2]) * per_point + h;
+      dst[x] = *src;
+    }
   }
 }
 
-template <typename T>
-__global__ void gc_reduce_kernel(GcDev d, T *__restrict__ out) {
-  const long long total = (long long)d.loc_n[0] * d.loc_n[1] * d.loc_n[2];
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const int j2 = (int)(p % d.loc_n[2]);
-    const long long q = p / d.loc_n[2];
-    const int j1 = (int)(q % d.loc_n[1]);
-    const int j0 = (int)(q / d.loc_n[1]);
-    for (int h = 0; h < d.tuple; h++) {
-      T acc = 0;
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) gc_reduce_kernel(GcDev d, T *__restrict__ out) {
+  struct alignas(sizeof(T) * VEC) V { T v[VEC]; };
+  const int rows = d.loc_n[0] * d.loc_n[1];
+  const int per_point = d.tuple / VEC;
+  const int row_vecs = d.loc_n[2] * per_point;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int j0 = row / d.loc_n[1], j1 = row - j0 * d.loc_n[1];
+    V *dst = reinterpret_cast<V *>(out) + (long long)row * row_vecs;
+    for (int x = threadIdx.x; x < row_vecs; x += blockDim.x) {
+      const int j2 = per_point == 1 ? x : x / per_point, h = per_point == 1 ? 0 : x - j2 * per_point;
+      V acc;
+#pragma unroll
+      for (int q = 0; q < VEC; q++) acc.v[q] = 0;
       for (int a = d.cp_off[0][j0]; a < d.cp_off[0][j0 + 1]; a++) {
         const int c0 = d.cp_c[0][a], i0 = d.cp_i[0][a];
         for (int b = d.cp_off[1][j1]; b < d.cp_off[1][j1 + 1]; b++) {
           const int c1 = d.cp_c[1][b], i1 = d.cp_i[1][b];
+          const long long i01 = (long long)i0 * d.ngc_of[1][c1] + i1;
+          const int rank01 = (c0 * d.np[1] + c1) * d.np[2];
           for (int c = d.cp_off[2][j2]; c < d.cp_off[2][j2 + 1]; c++) {
-            const int c2 = d.cp_c[2][c], i2 = d.cp_i[2][c];
-            const int rank = (c0 * d.np[1] + c1) * d.np[2] + c2;
-            const T *src = static_cast<const T *>(d.peer[rank]) +
-                           (((long long)i0 * d.ngc_of[1][c1] + i1) * d.ngc_of[2][c2] + i2) * d.tuple;
-            acc += src[h];
+            const int c2 = d.cp_c[2][c];
+            const V sv = *(reinterpret_cast<const V *>(d.peer[rank01 + c2]) + (i01 * d.ngc_of[2][c2] + d.cp_i[2][c]) * per_point + h);
+#pragma unroll
+            for (int q = 0; q < VEC; q++) acc.v[q] += sv.v[q];
           }
         }
       }
-      out[p * d.tuple + h] = acc;
+      dst[x] = acc;
     }
   }
 }
@@ -344,10 +362,19 @@ static void gc_run(GcPlan *g, bool reduce) {
   // 2. one kernel pulls everything it needs from the owners
   const size_t out_points = (reduce ? loc_elems : ngc_elems) / (size_t)g->tuple;
   if (out_points) {
-    const int threads = 256;
-    const long long blocks = std::min<long long>((long long)(out_points + threads - 1) / threads, 148 * 16);
-    if (reduce) gc_reduce_kernel<T><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
-    else gc_gather_kernel<T><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
+    const long long rows = reduce ? (long long)g->loc_n[0] * g->loc_n[1] : (long long)g->ngc[0] * g->ngc[1];
+    const int row_len = (int)((reduce ? g->loc_n[2] : g->ngc[2]) * g->tuple);
+    const int threads = row_len >= 256 ? 256 : (row_len >= 128 ? 128 : 64);
+    const long long blocks = std::min<long long>(rows, 148 * 16);
+    // whole grid points as one vector when a point is 1 or 2 reals (real / complex arrays without tuples)
+    const bool vec2 = g->tuple % 2 == 0 && (reinterpret_cast<uintptr_t>(data) % (2 * sizeof(T)) == 0);
+    if (reduce) {
+      if (vec2) gc_reduce_kernel<T, 2><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
+      else gc_reduce_kernel<T, 1><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
+    } else {
+      if (vec2) gc_gather_kernel<T, 2><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
+      else gc_gather_kernel<T, 1><<<(unsigned)blocks, threads, 0, st>>>(g->dev, data);
+    }
     launch_counter()++;
     GC_CUDA_OK(cudaGetLastError());
   }
