@@ -175,6 +175,8 @@ def nvlink_counters(index):
         out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
         tx = rx = 0
         seen = False
+        if os.environ.get("PFFT_BENCH_DEBUG"):
+            sys.stderr.write("nvidia-smi nvlink -gt d:\n" + out + "\n")
         for l in out.splitlines():
             l = l.strip()
             if "Data Tx" in l or "Data Rx" in l:
@@ -214,16 +216,19 @@ class ClockSampler:
                         self.reasons.add(nm)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.2)
 
     def __enter__(self):
+        if os.environ.get("PFFT_BENCH_NO_CLOCKS"):      # (experiments: rule out the sampler as a source of jitter)
+            return self
         self._thr = threading.Thread(target=self._run, daemon=True)
         self._thr.start()
         return self
 
     def __exit__(self, *a):
         self._stop.set()
-        self._thr.join(timeout=6)
+        if self._thr:
+            self._thr.join(timeout=6)
 
     def summary(self):
         s = sorted(self.samples)
@@ -496,16 +501,17 @@ def main():
         step(i)
     launches0 = pf.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms_f, stage_ms_b = [], []
-    barrier()
+    stage_ms_f, stage_ms_b, xch_ms = [], [], []
     nvl0 = nvlink_counters(local_rank) if (world > 1 and rank == 0) else None
     with ClockSampler(local_rank) as clk:
+        barrier()          # everything that could skew the ranks (sampler start, counter reads) is behind us
         ev0.record()
         for i in range(args.steps):
             fwd.execute()
             stage_ms_f.append(fwd.stage_times_ms())
             bwd.execute()
             stage_ms_b.append(bwd.stage_times_ms())
+            xch_ms.append(fwd.exchange_times_ms() + bwd.exchange_times_ms())
             if (args.warmup + i + 1) % rescale_every == 0:
                 a.mul_(2.0 ** (-rescale_every * growth))
         ev1.record()
@@ -581,7 +587,8 @@ def main():
     t_tr = ms_per_step / 2
     t_hbm = hbm_bytes / (peak * 1e9) * 1e3
     combined = {"hbm_bytes_per_gpu": hbm_bytes, "nvlink_bytes_per_gpu": nvl_bytes, "hbm_peak_gbs": peak,
-                "t_hbm_ms": t_hbm, "t_measured_ms": t_tr, "nvlink_gbs_in_exchange_stages": nvl_rates or None}
+                "t_hbm_ms": t_hbm, "t_measured_ms": t_tr, "nvlink_gbs_in_exchange_stages": nvl_rates or None,
+                "host_ms_ordering_exchanges_per_step": [sum(r[i] for r in xch_ms) / len(xch_ms) for i in range(len(xch_ms[0]))] if xch_ms and xch_ms[0] else None}
     if nvl0 and nvl1:
         # hardware counters of rank 0's GPU around the timed loop (forward + backward per step move 2 x nvl_bytes each way)
         combined["nvlink_counters_rank0"] = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / args.steps,

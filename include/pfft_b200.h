@@ -64,6 +64,8 @@ unsigned long long pfftb200_launch_count(void);
 /* per-stage device time of the last execute with timing enabled, milliseconds; returns #stages */
 void pfftb200_enable_stage_timing(const void *plan, int on);
 int pfftb200_stage_times(const void *plan, double *ms, int max_stages);
+/* host time spent ordering each exchange of the last blocking execute (barriers / flag waits), milliseconds */
+int pfftb200_exchange_times(const void *plan, double *ms, int max_exchanges);
 
 
 /* TEST SUPPORT (tests/test_kernel_emulation.py): stage `stage` of rank `pid`'s schedule run through the body

@@ -262,6 +262,11 @@ class Plan:
         n = lib().pfftb200_stage_times(self.handle, out, 64)
         return list(out)[:n]
 
+    def exchange_times_ms(self):
+        out = (C.c_double * 64)()
+        n = lib().pfftb200_exchange_times(self.handle, out, 64)
+        return list(out)[:n]
+
     def enable_stage_timing(self, on):
         lib().pfftb200_enable_stage_timing(self.handle, int(bool(on)))
 

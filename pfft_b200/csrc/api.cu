@@ -743,6 +743,14 @@ void pfftb200_enable_stage_timing(const void *plan, int on) {
   if (plan) const_cast<PlanBase *>(static_cast<const PlanBase *>(plan))->stage_timing = on != 0;
 }
 
+int pfftb200_exchange_times(const void *plan, double *ms, int max_exchanges) {
+  if (!plan) return 0;
+  const PlanBase *pl = static_cast<const PlanBase *>(plan);
+  int n = (int)pl->last_xch_ms.size();
+  for (int i = 0; i < n && i < max_exchanges; i++) ms[i] = pl->last_xch_ms[i];
+  return n;
+}
+
 int pfftb200_stage_times(const void *plan, double *ms, int max_stages) {
   if (!plan) return 0;
   const PlanBase *pl = static_cast<const PlanBase *>(plan);
