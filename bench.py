@@ -665,7 +665,7 @@ def main():
                 "vs_baseline": None, "dtype": cfg["prec"], "data": "synthetic (counter-based hash of the global index)",
                 "config": config, "roundtrip_rel_l2_err": rel, "spot_check": spot, "clocks": clk.summary(),
                 "gpu_launches": launches, "roofline": roofline, "roofline_hbm_nvlink": combined,
-                "transport": desc["transport"]}
+                "transport": desc["transport"], "exchange_ordering": desc.get("exchange_ordering")}
         if gcell:
             line["ghost_cells"] = gcell
         if e2e:

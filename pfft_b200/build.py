@@ -19,7 +19,8 @@ BUILD = os.path.join(ROOT, "build", "obj")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["minimpi.cpp", "decomp.cpp", "planner.cpp", "describe.cpp", "fft_tables.cpp",
-           "fft_generic.cu", "fft_mixed.cu", "fft_pow2.cu", "plan.cu", "transports.cu", "gcell.cu", "api.cu"]
+           "fft_generic.cu", "fft_mixed.cu", "fft_pow2.cu", "fft_reg.cu",
+           "fft_reg_k0_f64.cu", "fft_reg_k1_f64.cu", "fft_reg_k2_f64.cu", "fft_reg_k0_f32.cu", "fft_reg_k1_f32.cu", "fft_reg_k2_f32.cu", "plan.cu", "transports.cu", "gcell.cu", "api.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-I" + os.path.join(ROOT, "include"), "-I" + CSRC, "-I/usr/include"]

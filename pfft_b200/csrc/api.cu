@@ -704,13 +704,13 @@ size_t pfftb200_plan_describe(const void *plan, char *buf, size_t buflen) {
   std::string k = ",\"kernels\":[";
   for (size_t i = 0; i < pl->use_pow2.size(); i++) {
     k += i ? "," : "";
-    k += pl->kernel_kind[i] == KERNEL_POW2 ? "\"pow2\"" : (pl->kernel_kind[i] == KERNEL_MIXED ? "\"mixed\"" : "\"generic\"");
+    k += pl->kernel_kind[i] == KERNEL_POW2 ? "\"pow2\"" : (pl->kernel_kind[i] == KERNEL_REG ? "\"reg\"" : (pl->kernel_kind[i] == KERNEL_MIXED ? "\"mixed\"" : "\"generic\""));
   }
   k += "],\"kernel_names\":[";
   for (size_t i = 0; i < pl->params.size(); i++) {
     // the __global__ function the launchers pick for this stage (fft_pow2.cu: launch_stage_pow2 / launch_block_class)
     const StageParams &sp = pl->params[i];
-    const char *nm = pl->kernel_kind[i] == KERNEL_MIXED ? "stage_mixed_kernel" : "stage_generic_kernel";
+    const char *nm = pl->kernel_kind[i] == KERNEL_MIXED ? "stage_mixed_kernel" : (pl->kernel_kind[i] == KERNEL_REG ? "stage_reg_kernel" : "stage_generic_kernel");
     if (pl->use_pow2[i]) nm = sp.ntile > 0 ? "stage_blk_kernel" : ((sp.fast && sp.istride == 1) ? "fused_pair_kernel<FUSED=false>" : "stage_pow2_kernel");
     k += i ? "," : "";
     k += std::string("\"") + nm + "\"";
@@ -723,6 +723,8 @@ size_t pfftb200_plan_describe(const void *plan, char *buf, size_t buflen) {
   k += ",\"fused_tile_lines\":" + std::to_string(pl->fuse.possible ? pl->fuse.a.tl : 0);
   k += ",\"transport\":\"";
   k += pl->transport == TR_NCCL ? "nccl" : "p2p";
+  k += "\",\"exchange_ordering\":\"";
+  k += pl->transport == TR_NCCL ? "stream (nccl)" : (transport_device_sync(pl) ? "device flags" : "host barriers");
   k += "\"}";
   j = j.substr(0, j.size() - 1) + k;
   if (buf && buflen) {

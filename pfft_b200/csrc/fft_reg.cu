@@ -1,0 +1,197 @@
+// fft_reg.cu -- host side of the register-resident kernel for real lines and lengths 3 * 2^k
+// (fft_reg_kernel.h; instantiated per kind and precision in fft_reg_k*.cu): which stages it takes, tile and
+// shared-memory geometry, twiddle tables.
+#include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "kernels.h"
+
+namespace pfb {
+
+cudaError_t launch_reg_k0_f64(StageParams &sp, cudaStream_t stream);
+cudaError_t launch_reg_k1_f64(StageParams &sp, cudaStream_t stream);
+cudaError_t launch_reg_k2_f64(StageParams &sp, cudaStream_t stream);
+cudaError_t launch_reg_k0_f32(StageParams &sp, cudaStream_t stream);
+cudaError_t launch_reg_k1_f32(StageParams &sp, cudaStream_t stream);
+cudaError_t launch_reg_k2_f32(StageParams &sp, cudaStream_t stream);
+
+namespace {
+
+constexpr size_t kSmemLimit = 227 * 1024;
+
+// complex line length -> (sub-transform length, Q); the table of launch_reg_kind (fft_reg_kernel.h)
+bool reg_geometry(int NL, int kind, int *nsub, int *q) {
+  switch (NL) {
+    case 64: case 128: case 256: case 512: case 1024: case 2048:
+      if (kind == 0) return false;      // power-of-two complex lines belong to fft_pow2.cu
+      *nsub = NL;
+      *q = 1;
+      return true;
+    case 192: case 384: case 768: case 1536:
+      *nsub = NL / 3;
+      *q = 3;
+      return true;
+    default:
+      return false;
+  }
+}
+
+int floor_pow2_int(long long x) {
+  int p = 1;
+  while ((long long)p * 2 <= x) p *= 2;
+  return p;
+}
+
+int kind_of(const Stage &g) { return g.op == OP_R2C ? 1 : (g.op == OP_C2R ? 2 : 0); }
+
+}  // namespace
+
+template <typename T>
+bool reg_supported(const Stage &g, int L) {
+  static const bool off = [] {
+    const char *e = getenv("PFFT_B200_NO_REG");
+    return e && atoi(e) != 0;
+  }();
+  if (off || g.ntile > 0 || g.noseg > kMaxSeg) return false;
+  long long lines = 1;
+  for (int k = 0; k < g.nbatch; k++) {
+    if (g.batch[k].extent >= (1ll << 31)) return false;
+    lines *= g.batch[k].extent;
+  }
+  if (lines >= (1ll << 31)) return false;
+  auto all_even = [&](bool in_side) {
+    for (int k = 0; k < g.nbatch; k++)
+      if ((in_side ? g.batch[k].istride : g.batch[k].ostride) % 2) return false;
+    return true;
+  };
+  int NL = L;
+  const int kind = kind_of(g);
+  if (g.op == OP_C2C) {
+    if (g.in_real || g.out_real) return false;
+  } else if (g.op == OP_R2C) {
+    // packed pairs of reals: contiguous rows starting at even offsets, even window
+    if (!g.in_real || g.out_real || g.n % 2 || L != g.n) return false;
+    if (g.istride != 1 || g.iseg_stride != 0 || g.nin % 2 || g.zin % 2 || !all_even(true)) return false;
+    NL = (int)(g.n / 2);
+    if (g.zout < 0 || g.zout + g.nout > NL + 1) return false;
+  } else if (g.op == OP_C2R) {
+    if (g.in_real || !g.out_real || g.n % 2 || L != g.n) return false;
+    if (g.ostride != 1 || g.noseg != 1 || g.nout % 2 || g.zout % 2 || !all_even(false)) return false;
+    NL = (int)(g.n / 2);
+    if (g.zin < 0 || g.zin + g.nin > NL + 1) return false;
+  } else {
+    return false;
+  }
+  int nsub, q;
+  return reg_geometry(NL, kind, &nsub, &q);
+}
+
+template <typename T>
+bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, std::string *err) {
+  RegParams &rg = sp.rg;
+  memset(&rg, 0, sizeof rg);
+  rg.kind = kind_of(g);
+  rg.NL = rg.kind ? sp.n / 2 : sp.L;
+  int nsub = 0, Q = 1;
+  if (!reg_geometry(rg.NL, rg.kind, &nsub, &Q)) {
+    *err = "internal: length not served by the register-resident kernel";
+    return false;
+  }
+  const int E = pow2_points_per_thread(nsub);
+  const int TL = Q * nsub / E;
+  const size_t csize = 2 * sizeof(T);
+  // ---- tile: lines per CTA.  A strided side wants long runs (tl elements per point), contiguous sides two CTAs per SM
+  const bool strided = (rg.kind != 1 && g.istride != 1) || (rg.kind != 2 && g.ostride != 1);
+  static const int forced = [] {
+    const char *e = getenv("PFFT_B200_REG_TL");
+    return e ? atoi(e) : 0;
+  }();
+  int tl = std::max(1, floor_pow2_int((strided ? 512 : 256) / TL));
+  if (forced > 0) tl = floor_pow2_int(forced);
+  while (tl > 1 && tl * TL > 512) tl /= 2;
+  if (g.tile_dim < 0) tl = 1;
+  else if ((INT)tl > g.batch[g.tile_dim].extent) tl = floor_pow2_int(std::max<INT>(1, g.batch[g.tile_dim].extent));
+  // ---- buffer line: the Q sub-line regions resp. the padded natural-order line (+ the Nyquist bin of c2r input)
+  const int RS = Q == 1 ? nsub + (nsub >> 4) : ((nsub + (nsub >> 4) + 7) / 8 * 8 + 3);
+  using std::max;
+  const int P1 = E, rem1 = nsub / E, P2 = rem1 >= E ? E : rem1, P3 = rem1 / P2;
+  const int twn = (P2 - 1) * P1 + (P3 > 1 ? (P3 - 1) * P1 * P2 : 0) + (Q > 1 ? rg.NL : 0) + (rg.kind ? rg.NL + 1 : 0);
+  for (;;) {
+    const int base = (max(Q * RS, rg.NL + (rg.NL >> 4) + 1) + 7) / 8 * 8;
+    rg.pitch = base + (tl >= 8 ? 1 : 8 / tl);       // lines of a tile start in different banks (tile-minor accesses)
+    const size_t buf = (size_t)tl * rg.pitch * csize, tab = (size_t)twn * csize;
+    if (buf + tab > kSmemLimit && tl > 1) {
+      tl /= 2;
+      continue;
+    }
+    if (buf + tab > kSmemLimit) {
+      *err = "internal: line does not fit the register-resident kernel";
+      return false;
+    }
+    // inputs into a buffer of their own when that does not cost a resident CTA
+    const int ctas = tl * TL <= 256 ? 2 : 1;
+    static const int sep_env = [] {
+      const char *e = getenv("PFFT_B200_REG_SEPARATE");
+      return e ? atoi(e) : -1;
+    }();
+    rg.separate = (2 * buf + tab + 1024 <= kSmemLimit / ctas) ? 1 : 0;
+    if (sep_env == 0) rg.separate = 0;
+    if (sep_env == 1 && 2 * buf + tab <= kSmemLimit) rg.separate = 1;
+    break;
+  }
+  sp.tl = tl;
+  sp.line_bars = 1;
+  rg.diblk = make_fastdiv((unsigned)std::max(1, sp.iblk));
+  rg.doblk = make_fastdiv((unsigned)std::max(1, sp.oblk));
+  // ---- tables: [pass 2 | pass 3 of the sub-transform | w_NL^m | w_n^k], rounded once from fp64 roots
+  std::vector<double> all;
+  {
+    std::vector<double> roots(2 * (size_t)nsub), pp;
+    make_twiddles_f64(nsub, roots.data());
+    size_t off2 = 0, off3 = 0;
+    pow2_twiddle_tables(nsub, roots.data(), &pp, &off2, &off3);
+    all.insert(all.end(), pp.begin(), pp.end());
+  }
+  if (Q > 1) {
+    std::vector<double> roots(2 * (size_t)rg.NL);
+    make_twiddles_f64(rg.NL, roots.data());
+    all.insert(all.end(), roots.begin(), roots.end());
+  }
+  if (rg.kind) {
+    std::vector<double> roots(4 * (size_t)rg.NL);
+    make_twiddles_f64(2 * rg.NL, roots.data());
+    all.insert(all.end(), roots.begin(), roots.begin() + 2 * (size_t)(rg.NL + 1));
+  }
+  if ((int)(all.size() / 2) != twn) {
+    *err = "internal: twiddle table size mismatch";
+    return false;
+  }
+  std::vector<T> host(all.begin(), all.end());
+  rg.tables = upload(host.data(), host.size() * sizeof(T), ctx);
+  return true;
+}
+
+template <typename T>
+cudaError_t launch_stage_reg(StageParams &sp, cudaStream_t stream) {
+  if (sp.ntiles <= 0) return cudaSuccess;
+  if (sp.ntiles >= (1ll << 31)) return cudaErrorInvalidValue;
+  const bool f64 = sizeof(T) == 8;
+  switch (sp.rg.kind) {
+    case 0: return f64 ? launch_reg_k0_f64(sp, stream) : launch_reg_k0_f32(sp, stream);
+    case 1: return f64 ? launch_reg_k1_f64(sp, stream) : launch_reg_k1_f32(sp, stream);
+    default: return f64 ? launch_reg_k2_f64(sp, stream) : launch_reg_k2_f32(sp, stream);
+  }
+}
+
+template bool reg_supported<float>(const Stage &, int);
+template bool reg_supported<double>(const Stage &, int);
+template bool reg_prepare<float>(const Stage &, StageParams &, UploadFn, void *, std::string *);
+template bool reg_prepare<double>(const Stage &, StageParams &, UploadFn, void *, std::string *);
+template cudaError_t launch_stage_reg<float>(StageParams &, cudaStream_t);
+template cudaError_t launch_stage_reg<double>(StageParams &, cudaStream_t);
+
+}  // namespace pfb

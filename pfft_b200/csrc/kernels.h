@@ -57,6 +57,16 @@ struct MixedParams {
   long long ws_stride;       // complex elements per CTA
 };
 
+// register-resident kernel for real lines and lengths 3 * 2^k (fft_reg_kernel.h)
+struct RegParams {
+  int NL;                    // complex points per line: n, or n / 2 for real lines
+  int kind;                  // 0 complex, 1 r2c, 2 c2r
+  int pitch;                 // complex elements per buffer line
+  int separate;              // inputs are fetched into a buffer of their own (double buffering)
+  FastDiv diblk, doblk;
+  const void *tables;        // [pass-2 | pass-3 twiddles of the sub-transform | w_NL^m (Q > 1) | w_n^k, k <= n/2 (real lines)]
+};
+
 // Plain-old-data copy of a Stage plus pointers; passed to kernels by value.
 struct StageParams {
   const void *in;
@@ -101,6 +111,7 @@ struct StageParams {
   long long out_off[16];     // ... on output, inside chunk out_seg[e]
   int out_seg[16];
   MixedParams mx;
+  RegParams rg;
 };
 
 // Plane-fused pair of stages (fft_pow2.cu: fused_pair_kernel).
@@ -155,6 +166,14 @@ int fused_pick_tile(int L);
 template <typename T>
 cudaError_t launch_fused_pow2(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream);
 void pow2_twiddle_tables(int L, const double *roots, std::vector<double> *table, size_t *off2, size_t *off3);
+
+// real lines (packed half-length transforms) and complex lines of length 3 * 2^k held in registers (fft_reg.cu)
+template <typename T>
+bool reg_supported(const Stage &g, int L);
+template <typename T>
+bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, std::string *err);
+template <typename T>
+cudaError_t launch_stage_reg(StageParams &sp, cudaStream_t stream);
 
 unsigned long long &launch_counter();
 

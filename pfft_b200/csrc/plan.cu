@@ -109,7 +109,9 @@ template void *make_r2r_table<double>(int, UploadFn, void *);
 
 // Kernel family of every stage and its parameters:
 //   pow2   power-of-two complex lines, 64..4096, held in registers (fft_pow2.cu; the headline path)
-//   mixed  everything else: any length, real lines, DCT/DST, copy stages (fft_mixed.cu)
+//   reg    real lines of length 2 * {2^k, 3 * 2^k} as packed half-length transforms and complex lines of
+//          length 3 * 2^k, held in registers (fft_reg.cu)
+//   mixed  everything else: any length, odd real lines, DCT/DST, copy stages (fft_mixed.cu)
 //   generic  the round-1 any-length kernel, kept behind PFFT_B200_GENERIC=1 for A/B comparisons
 template <typename T>
 static bool build_stage_params(PlanBase *pl, std::string *err) {
@@ -130,12 +132,16 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     const int L = sp.L;
     const bool fast = pow2_supported<T>(g, L);
     int kind = fast ? KERNEL_POW2 : (old_generic ? KERNEL_GENERIC : KERNEL_MIXED);
+    if (kind == KERNEL_MIXED && reg_supported<T>(g, L)) kind = KERNEL_REG;
     if (g.op == OP_R2R) {
       auto jt = table_of.find(-8 * sp.r2r_D);
       if (jt == table_of.end()) jt = table_of.emplace(-8 * sp.r2r_D, TableSet{make_r2r_table<T>(sp.r2r_D, upload_device, pl), 0, 0}).first;
       sp.tw_r2r = jt->second.dev;
     }
-    if (kind == KERNEL_MIXED) {
+    if (kind == KERNEL_REG) {
+      if (!reg_prepare<T>(g, sp, upload_device, pl, err)) return false;
+      stage_params_tiles(g, sp, sp.tl);
+    } else if (kind == KERNEL_MIXED) {
       if (!mixed_prepare<T>(g, sp, upload_device, pl, err)) return false;
       stage_params_tiles(g, sp, sp.tl);
     } else {
@@ -675,6 +681,8 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
     }
   };
   double xch_host[16] = {0};
+  const bool dsync = transport_device_sync(pl);
+  if (dsync) transport_begin_execute(pl);
   for (size_t i = 0; i < nst; i++) {
     const Stage &g = s.stages[i];
     StageParams sp = pl->params[i];
@@ -709,7 +717,9 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
       break;
     }
     double t0 = 0;
-    if (xch) {
+    if (dsync) {
+      transport_wait_stage(pl, (int)i);
+    } else if (xch) {
       t0 = MPI_Wtime();
       transport_before_stage(pl, (int)i);
       xch_host[g.exchange % 16] += MPI_Wtime() - t0;
@@ -720,14 +730,20 @@ void plan_execute(PlanBase *pl, void *in, void *out, bool blocking) {
       const int kk = pl->kernel_kind[i];
       if (pl->prec == PREC_F64)
         e = kk == KERNEL_POW2 ? launch_stage_pow2<double>(sp, st)
-                              : (kk == KERNEL_MIXED ? launch_stage_mixed<double>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st) : launch_stage_generic<double>(sp, st));
+            : kk == KERNEL_REG ? launch_stage_reg<double>(sp, st)
+            : kk == KERNEL_MIXED ? launch_stage_mixed<double>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st)
+                                 : launch_stage_generic<double>(sp, st);
       else
         e = kk == KERNEL_POW2 ? launch_stage_pow2<float>(sp, st)
-                              : (kk == KERNEL_MIXED ? launch_stage_mixed<float>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st) : launch_stage_generic<float>(sp, st));
+            : kk == KERNEL_REG ? launch_stage_reg<float>(sp, st)
+            : kk == KERNEL_MIXED ? launch_stage_mixed<float>(sp, &pl->mixed_ws, &pl->mixed_ws_bytes, st)
+                                 : launch_stage_generic<float>(sp, st);
       CUDA_OK(e);
     }
     if (pl->stage_timing) cudaEventRecord(pl->events[2 * i + 1], st);
-    if (xch) {
+    if (dsync) {
+      transport_signal_stage(pl, (int)i);
+    } else if (xch) {
       t0 = MPI_Wtime();
       transport_after_stage(pl, (int)i);
       xch_host[g.exchange % 16] += MPI_Wtime() - t0;

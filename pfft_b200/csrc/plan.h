@@ -13,7 +13,7 @@ namespace pfb {
 
 enum Precision : int { PREC_F64 = 0, PREC_F32 = 1 };
 enum TransportKind : int { TR_AUTO = 0, TR_NCCL = 1, TR_P2P = 2 };
-enum KernelKind : int { KERNEL_GENERIC = 0, KERNEL_POW2 = 1, KERNEL_MIXED = 2 };
+enum KernelKind : int { KERNEL_GENERIC = 0, KERNEL_POW2 = 1, KERNEL_MIXED = 2, KERNEL_REG = 3 };
 
 // Same fields as the reference's timer (kernel/ipfft.h:208-219) so that
 // pfft_convert_timer2vec keeps its documented layout (kernel/timer.c:297-319).
@@ -107,6 +107,11 @@ bool transport_setup(PlanBase *pl, std::string *err);
 void transport_teardown(PlanBase *pl);
 // resolve the output base pointers of a stage followed by exchange `x` (before launching it)
 void transport_stage_outputs(PlanBase *pl, int stage_idx, void **out_ptrs);
+// device-side ordering of the p2p transport (every rank on a GPU of its own): no host synchronisation
+bool transport_device_sync(const PlanBase *pl);
+void transport_begin_execute(PlanBase *pl);
+void transport_wait_stage(PlanBase *pl, int stage_idx);
+void transport_signal_stage(PlanBase *pl, int stage_idx);
 void transport_before_stage(PlanBase *pl, int stage_idx);
 void transport_after_stage(PlanBase *pl, int stage_idx);
 

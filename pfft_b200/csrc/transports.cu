@@ -8,13 +8,18 @@
 //         barrier over the mesh dimension's communicator before ("receive areas are
 //         free") and after ("all chunks have landed") the stage.  Also works between
 //         ranks that share one GPU, which is how multi-rank plans are tested on a
-//         single-GPU box.
+//         single-GPU box.  When every rank of the plan has a GPU of its own the ordering
+//         is done ON THE DEVICE instead (progress counters in peer-mapped memory, a
+//         one-CTA signal kernel behind every stage and a one-CTA wait kernel in front of
+//         the stages that need it): no host synchronisation, the whole transform is
+//         stream-ordered and pfftb200_execute_async really is asynchronous.
 //  nccl : the stage writes per-destination chunks into a send area and a grouped
 //         ncclSend/ncclRecv all-to-all(v) moves them, stream-ordered, no host sync.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -30,7 +35,15 @@ struct PeerMap {
   std::vector<void *> opened;   // to close
   // cart rank of member q of mesh dimension m
   std::vector<int> member_rank[kMaxGroups];
+  // device-side ordering (see the head of this file): flags[0] = number of executes started,
+  // flags[kFlagBase + r] = progress of cart rank r as r itself wrote it: 64 * execute + stages completed
+  bool dev_sync = false;
+  unsigned *flags = nullptr;
+  unsigned **peer_flags_dev = nullptr;   // device array [np]: rank r's flags (null: not a peer, or self)
+  int me = 0, np = 1;
 };
+constexpr int kFlagBase = 16, kFlagWords = 256;
+constexpr size_t kFlagBytes = (size_t)2 << 20;   // an allocation of its own (IPC handles map whole allocations)
 
 namespace {
 
@@ -75,6 +88,45 @@ std::map<std::vector<int>, ncclComm_t> &nccl_cache() {
   return c;
 }
 
+// ---- device-side ordering kernels -----------------------------------------------------------
+struct WaitList {
+  int n;
+  int rank[2 * kMaxSeg];
+  int back[2 * kMaxSeg];        // 1: the target lies in the previous execute
+  unsigned code[2 * kMaxSeg];   // stages completed
+};
+__global__ void xch_begin_kernel(unsigned *flags) { flags[0] += 1u; }
+__global__ void xch_signal_kernel(const unsigned *flags, unsigned *const *peer, int me, int np, unsigned code) {
+  const int r = threadIdx.x;
+  if (r >= np || !peer[r]) return;
+  const unsigned v = flags[0] * 64u + code;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer[r] + kFlagBase + me), "r"(v) : "memory");
+}
+__global__ void xch_wait_kernel(const unsigned *flags, const __grid_constant__ WaitList w) {
+  const int i = threadIdx.x;
+  if (i >= w.n) return;
+  const unsigned target = (flags[0] - (unsigned)w.back[i]) * 64u + w.code[i];
+  const unsigned *p = flags + kFlagBase + w.rank[i];
+  unsigned long long t0 = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (unsigned spins = 0;; spins++) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if ((int)(v - target) >= 0) break;
+    __nanosleep(200);
+    if ((spins & 0xfff) == 0xfff) {
+      // a peer that never arrives (crashed rank, mismatched sequence of executes) must not hang the GPU for good
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t1 - t0 > 60ull * 1000000000ull) {
+        printf("pfft_b200: gave up waiting for rank %d (progress %u, wanted %u)\n", w.rank[i], v, target);
+        break;
+      }
+    }
+  }
+}
+
 void fill_members(PlanBase *pl) {
   PeerMap *pm = pl->peers;
   const Schedule &s = pl->sched;
@@ -92,10 +144,27 @@ bool transport_setup(PlanBase *pl, std::string *err) {
   bool ok = true;
   if (pl->transport == TR_P2P) {
     struct Handles {
-      cudaIpcMemHandle_t h[2];
-      int has[2];
+      cudaIpcMemHandle_t h[3];   // receive areas A, B and the ordering flags
+      int has[3];
+      char bus_id[32];           // which GPU this rank drives
     } mine, *all;
     memset(&mine, 0, sizeof mine);
+    PeerMap *pm = pl->peers;
+    pm->me = me;
+    pm->np = np;
+    {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetPCIBusId(mine.bus_id, (int)sizeof mine.bus_id, dev);
+      // progress of every rank starts as "execute 0 complete"
+      std::vector<unsigned> init(kFlagWords, 0u);
+      for (int r = 0; r < kFlagWords - kFlagBase; r++) init[kFlagBase + r] = 63u;
+      if (np <= kFlagWords - kFlagBase && cudaMalloc(&pm->flags, kFlagBytes) == cudaSuccess) {
+        cudaMemcpy(pm->flags, init.data(), kFlagWords * sizeof(unsigned), cudaMemcpyHostToDevice);
+        mine.has[2] = cudaIpcGetMemHandle(&mine.h[2], pm->flags) == cudaSuccess ? 1 : 0;
+      }
+      cudaGetLastError();
+    }
     for (int b = 0; b < 2; b++) {
       mine.has[b] = pl->scratch[b] != nullptr;
       if (mine.has[b]) {
@@ -132,6 +201,37 @@ bool transport_setup(PlanBase *pl, std::string *err) {
         pl->peers->opened.push_back(p);
       }
     }
+    // device-side ordering needs a GPU per rank (a waiting kernel must never keep a peer's kernels off
+    // the GPU they share) and few enough stages for the progress code
+    const char *env = getenv("PFFT_B200_P2P_SYNC");
+    bool dsync = ok && !(env && !strcmp(env, "host")) && np <= 64 && pl->sched.stages.size() < 60;
+    for (int rk = 0; rk < np && dsync; rk++) {
+      if (all[rk].has[2] <= 0) dsync = false;
+      for (int r2 = 0; r2 < rk && dsync; r2++)
+        if (!strncmp(all[rk].bus_id, all[r2].bus_id, sizeof mine.bus_id)) dsync = false;
+    }
+    if (dsync) {
+      std::vector<unsigned *> pf(np, nullptr);
+      for (int rk = 0; rk < np && dsync; rk++) {
+        if (rk == me || !is_peer[rk]) continue;
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, all[rk].h[2], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          cudaGetLastError();
+          dsync = false;
+          break;
+        }
+        pf[rk] = static_cast<unsigned *>(p);
+        pm->opened.push_back(p);
+      }
+      if (dsync && cudaMalloc(&pm->peer_flags_dev, np * sizeof(unsigned *)) == cudaSuccess)
+        cudaMemcpy(pm->peer_flags_dev, pf.data(), np * sizeof(unsigned *), cudaMemcpyHostToDevice);
+      else
+        dsync = false;
+    }
+    // all ranks or none
+    int mine_ok = dsync ? 1 : 0, all_ok = 0;
+    MPI_Allreduce(&mine_ok, &all_ok, 1, MPI_INT, MPI_MIN, pl->comm_cart);
+    pm->dev_sync = all_ok != 0;
     delete[] all;
   } else {
     NcclApi &api = nccl();
@@ -162,7 +262,14 @@ bool transport_setup(PlanBase *pl, std::string *err) {
 
 void transport_teardown(PlanBase *pl) {
   if (!pl->peers) return;
+  if (pl->transport == TR_P2P) {
+    // peers may still be storing into my receive areas or flags
+    cudaStreamSynchronize(pl->stream);
+    MPI_Barrier(pl->comm_cart);
+  }
   for (void *p : pl->peers->opened) cudaIpcCloseMemHandle(p);
+  if (pl->peers->flags) cudaFree(pl->peers->flags);
+  if (pl->peers->peer_flags_dev) cudaFree(pl->peers->peer_flags_dev);
   delete pl->peers;
   pl->peers = nullptr;
 }
@@ -182,6 +289,55 @@ void transport_stage_outputs(PlanBase *pl, int i, void **out) {
       out[q] = static_cast<char *>(pl->scratch[2]) + (size_t)g.oseg_off[q] * es;
     }
   }
+}
+
+bool transport_device_sync(const PlanBase *pl) { return pl->peers && pl->transport == TR_P2P && pl->peers->dev_sync; }
+
+void transport_begin_execute(PlanBase *pl) {
+  xch_begin_kernel<<<1, 1, 0, pl->stream>>>(pl->peers->flags);
+}
+
+// Device-side ordering in front of stage i:
+//  (a) its input was stored by the members of an exchange group: all of them must have completed stage i - 1;
+//  (b) it stores into its peers' receive area b: every peer must have completed the stage that consumed what
+//      area b held before -- stage j + 1, j the previous boundary kept in b (in this execute, else the last one
+//      of the previous execute).
+void transport_wait_stage(PlanBase *pl, int i) {
+  const Schedule &s = pl->sched;
+  PeerMap *pm = pl->peers;
+  WaitList w;
+  w.n = 0;
+  auto add_group = [&](int xi, int back, unsigned code) {
+    const Exchange &x = s.exchanges[xi];
+    for (int q = 0; q < x.nparts; q++) {
+      if (q == x.me || w.n >= 2 * kMaxSeg) continue;
+      w.rank[w.n] = pm->member_rank[x.mesh_dim][q];
+      w.back[w.n] = back;
+      w.code[w.n] = code;
+      w.n++;
+    }
+  };
+  const int nb = (int)pl->boundary_remote.size();
+  if (i > 0 && pl->boundary_remote[i - 1]) add_group(s.stages[i - 1].exchange, 0, (unsigned)i);
+  if (i < nb && pl->boundary_remote[i]) {
+    const int b = pl->assign[i];
+    int j = -1;
+    for (int k = i - 1; k >= 0; k--)
+      if (pl->assign[k] == b) { j = k; break; }
+    if (j >= 0) {
+      add_group(s.stages[i].exchange, 0, (unsigned)(j + 2));
+    } else {
+      for (int k = nb - 1; k >= 0; k--)
+        if (pl->assign[k] == b) { j = k; break; }
+      add_group(s.stages[i].exchange, 1, (unsigned)(j + 2));
+    }
+  }
+  if (w.n > 0) xch_wait_kernel<<<1, 2 * kMaxSeg, 0, pl->stream>>>(pm->flags, w);
+}
+
+void transport_signal_stage(PlanBase *pl, int i) {
+  PeerMap *pm = pl->peers;
+  xch_signal_kernel<<<1, 64, 0, pl->stream>>>(pm->flags, pm->peer_flags_dev, pm->me, pm->np, (unsigned)(i + 1));
 }
 
 void transport_before_stage(PlanBase *pl, int i) {

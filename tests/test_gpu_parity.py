@@ -96,6 +96,35 @@ SINGLE_RANK = [
     dict(kind="r2r", n=[16, 16, 16], np=[1, 1], kinds=[po.REDFT10, po.REDFT10, po.REDFT10], precision="single"),
     dict(kind="r2r", n=[12, 10, 9], ni=[6, 5, 4], no=[12, 10, 9], np=[1, 1], kinds=[po.REDFT00, po.RODFT00, po.REDFT01]),
     dict(kind="r2r", n=[64, 32, 128], np=[1, 1], kinds=[po.REDFT10, po.RODFT10, po.REDFT01], flags=T_OUT),
+    # register-resident kernel for real lines (packed half-length transforms) and lengths 3 * 2^k (fft_reg_kernel.h)
+    dict(kind="r2c", n=[8, 4, 2048], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[8, 4, 2048], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[4, 8, 4096], np=[1, 1], tag="-reg"),
+    dict(kind="c2r", n=[4, 8, 4096], np=[1, 1], sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[16, 8, 512], np=[1, 1], flags=T_OUT | PAD, tag="-reg"),
+    dict(kind="c2r", n=[16, 8, 512], np=[1, 1], flags=T_IN | PAD, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[8, 8, 1024], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[8, 8, 1024], np=[1, 1], flags=T_IN, sign=+1, precision="single", tag="-reg"),
+    dict(kind="r2c", n=[8, 16, 256], ni=[8, 16, 128], no=[8, 16, 256], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[8, 16, 256], ni=[8, 16, 256], no=[8, 16, 128], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[8, 16, 256], ni=[8, 16, 128], no=[8, 16, 256], np=[1, 1], flags=S_IN | S_OUT, tag="-reg"),
+    dict(kind="c2c", n=[4, 8, 768], np=[1, 1], tag="-reg"),
+    dict(kind="c2c", n=[4, 8, 768], np=[1, 1], sign=+1, flags=T_OUT, tag="-reg"),
+    dict(kind="c2c", n=[768, 4, 8], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2c", n=[8, 384, 16], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2c", n=[8, 16, 192], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="c2c", n=[4, 4, 1536], np=[1, 1], flags=T_OUT, precision="single", tag="-reg"),
+    dict(kind="c2c", n=[8, 768, 12], ni=[8, 512, 8], no=[8, 768, 12], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2c", n=[8, 768, 12], ni=[8, 768, 12], no=[8, 512, 8], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="c2c", n=[8, 4, 768], ni=[8, 4, 512], no=[8, 4, 768], np=[1, 1], flags=S_IN | S_OUT, tag="-reg"),
+    dict(kind="r2c", n=[8, 4, 768], np=[1, 1], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[8, 4, 768], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[4, 8, 384], np=[1, 1], flags=T_OUT | PAD, precision="single", tag="-reg"),
+    dict(kind="c2r", n=[4, 8, 384], np=[1, 1], flags=T_IN | PAD, sign=+1, precision="single", tag="-reg"),
+    dict(kind="r2c", n=[4, 4, 1536], np=[1, 1], tag="-reg"),
+    dict(kind="c2r", n=[4, 4, 3072], np=[1, 1], sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[12, 12, 768], ni=[8, 8, 512], no=[12, 12, 768], np=[1, 1], flags=T_OUT, tag="-reg"),       # config 5 in small
+    dict(kind="c2r", n=[12, 12, 768], ni=[12, 12, 768], no=[8, 8, 512], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
     # plane-fused last pair (power-of-two lines of equal length in the last two stages)
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_OUT, tag="-fused"),
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
@@ -122,6 +151,8 @@ def test_single_rank_matches_oracle(world, case):
     assert err < TOL[case.get("precision", "double")], err
     assert l2 < TOL_L2[case.get("precision", "double")], l2
     assert res["input_preserved"], "out-of-place plans must not touch the input (PFFT_PRESERVE_INPUT default)"
+    if case.get("tag") == "-reg":
+        assert "reg" in res["kernels"], res["kernels"]
     if case.get("tag") == "-fused" and case.get("precision", "double") == "double" and os.environ.get("PFFT_B200_FUSE", "0") == "1":
         assert res["fused"] == 1, "expected the plane-fused pair kernel for this case"
 
@@ -149,6 +180,13 @@ MULTI_RANK = [
     dict(kind="c2r", n=[8, 16, 128], np=[2, 2], flags=S_OUT, sign=+1),
     dict(kind="c2r", n=[8, 16, 128], np=[2, 2], flags=S_IN | S_OUT | T_IN, sign=+1),
     dict(kind="r2c", n=[8, 16, 128], np=[2, 2], flags=S_IN | S_OUT | T_OUT),
+    # register-resident real lines / 3 * 2^k lengths across exchanges (segmented outputs, gathered inputs)
+    dict(kind="r2c", n=[16, 16, 512], np=[2, 2], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[16, 16, 512], np=[2, 2], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[8, 768, 768], ni=[8, 512, 512], no=[8, 768, 768], np=[2, 2], flags=T_OUT, tag="-reg"),
+    dict(kind="c2r", n=[8, 768, 768], ni=[8, 768, 768], no=[8, 512, 512], np=[2, 2], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="c2c", n=[384, 12, 192], np=[2, 2], tag="-reg"),
+    dict(kind="c2c", n=[384, 12, 192], np=[3], flags=T_OUT, precision="single", tag="-reg"),
     # micro-blocked chains of power-of-two stages across exchanges
     dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_OUT, tag="-blk"),
     dict(kind="c2c", n=[64, 64, 64], np=[2, 2], flags=T_IN, sign=+1, tag="-blk"),
