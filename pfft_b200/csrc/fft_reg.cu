@@ -23,21 +23,48 @@ namespace {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-// complex line length -> (sub-transform length, Q); the table of launch_reg_kind (fft_reg_kernel.h)
-bool reg_geometry(int NL, int kind, int *nsub, int *q) {
+// complex line length -> (sub-transform length, points per thread, Q); the table of launch_reg_kind (fft_reg_kernel.h)
+bool reg_geometry(int NL, int kind, int *nsub, int *E, int *q) {
   switch (NL) {
     case 64: case 128: case 256: case 512: case 1024: case 2048:
       if (kind == 0) return false;      // power-of-two complex lines belong to fft_pow2.cu
       *nsub = NL;
       *q = 1;
-      return true;
+      break;
     case 192: case 384: case 768: case 1536:
       *nsub = NL / 3;
       *q = 3;
-      return true;
+      break;
     default:
       return false;
   }
+  *E = *nsub <= 512 ? 8 : 16;
+  return true;
+}
+
+// threads per CTA the kernel is compiled for (launch_reg_one)
+template <typename T>
+int reg_class(int E, int Q) {
+  return E == 8 ? ((sizeof(T) == 4 && Q == 1) ? 1024 : 768) : 512;
+}
+
+// per-pass twiddle tables [r-1][k] of the sub-transform (same layout as pow2_twiddle_tables, for a given E)
+void reg_pass_tables(int L, int E, const double *roots, std::vector<double> *table) {
+  int rem = L / E;
+  const int R1 = E, R2 = rem >= E ? E : rem;
+  rem /= R2;
+  const int R3 = rem;
+  auto emit = [&](int NS, int R) {
+    const int tstep = L / (NS * R);
+    for (int r = 1; r < R; r++)
+      for (int k = 0; k < NS; k++) {
+        const long long idx = (long long)k * r * tstep;
+        table->push_back(roots[2 * idx]);
+        table->push_back(roots[2 * idx + 1]);
+      }
+  };
+  emit(R1, R2);
+  if (R3 > 1) emit(R1 * R2, R3);
 }
 
 int floor_pow2_int(long long x) {
@@ -86,8 +113,8 @@ bool reg_supported(const Stage &g, int L) {
   } else {
     return false;
   }
-  int nsub, q;
-  return reg_geometry(NL, kind, &nsub, &q);
+  int nsub, E, q;
+  return reg_geometry(NL, kind, &nsub, &E, &q);
 }
 
 template <typename T>
@@ -96,25 +123,25 @@ bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, st
   memset(&rg, 0, sizeof rg);
   rg.kind = kind_of(g);
   rg.NL = rg.kind ? sp.n / 2 : sp.L;
-  int nsub = 0, Q = 1;
-  if (!reg_geometry(rg.NL, rg.kind, &nsub, &Q)) {
+  int nsub = 0, Q = 1, E = 8;
+  if (!reg_geometry(rg.NL, rg.kind, &nsub, &E, &Q)) {
     *err = "internal: length not served by the register-resident kernel";
     return false;
   }
-  const int E = pow2_points_per_thread(nsub);
   const int TL = Q * nsub / E;
   const size_t csize = 2 * sizeof(T);
-  // ---- tile: lines per CTA.  A strided side wants long runs (tl elements per point), contiguous sides two CTAs per SM
-  const bool strided = (rg.kind != 1 && g.istride != 1) || (rg.kind != 2 && g.ostride != 1);
+  rg.E = E;
+  rg.maxt = reg_class<T>(E, Q);
+  // ---- tile: as many lines as the thread class holds -- one persistent CTA per SM with a staging buffer of its own,
+  // all of its warps needed to cover latency; a strided side then moves tl elements per point in one run
   static const int forced = [] {
     const char *e = getenv("PFFT_B200_REG_TL");
     return e ? atoi(e) : 0;
   }();
-  int tl = std::max(1, floor_pow2_int((strided ? 512 : 256) / TL));
-  if (forced > 0) tl = floor_pow2_int(forced);
-  while (tl > 1 && tl * TL > 512) tl /= 2;
+  int tl = std::max(1, rg.maxt / TL);
+  if (forced > 0) tl = std::min(forced, tl);
   if (g.tile_dim < 0) tl = 1;
-  else if ((INT)tl > g.batch[g.tile_dim].extent) tl = floor_pow2_int(std::max<INT>(1, g.batch[g.tile_dim].extent));
+  else if ((INT)tl > g.batch[g.tile_dim].extent) tl = (int)std::max<INT>(1, g.batch[g.tile_dim].extent);
   // ---- buffer line: the Q sub-line regions resp. the padded natural-order line (+ the Nyquist bin of c2r input)
   const int RS = Q == 1 ? nsub + (nsub >> 4) : ((nsub + (nsub >> 4) + 7) / 8 * 8 + 3);
   using std::max;
@@ -122,29 +149,26 @@ bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, st
   const int twn = (P2 - 1) * P1 + (P3 > 1 ? (P3 - 1) * P1 * P2 : 0) + (Q > 1 ? rg.NL : 0) + (rg.kind ? rg.NL + 1 : 0);
   for (;;) {
     const int base = (max(Q * RS, rg.NL + (rg.NL >> 4) + 1) + 7) / 8 * 8;
-    rg.pitch = base + (tl >= 8 ? 1 : 8 / tl);       // lines of a tile start in different banks (tile-minor accesses)
-    const size_t buf = (size_t)tl * rg.pitch * csize, tab = (size_t)twn * csize;
-    if (buf + tab > kSmemLimit && tl > 1) {
-      tl /= 2;
-      continue;
-    }
-    if (buf + tab > kSmemLimit) {
+    rg.pitch = base + (tl >= 8 ? 1 : (tl >= 4 ? 2 : (tl >= 2 ? 4 : 0)));   // lines of a tile start in different banks (tile-minor accesses)
+    rg.spitch = (rg.NL + 2) | 1;                    // dense staging lines (+ the Nyquist bin), odd pitch
+    const size_t need = ((size_t)tl * (rg.pitch + rg.spitch) + twn) * csize;
+    if (need <= kSmemLimit) break;
+    if (tl == 1) {
       *err = "internal: line does not fit the register-resident kernel";
       return false;
     }
-    // inputs into a buffer of their own when that does not cost a resident CTA
-    const int ctas = tl * TL <= 256 ? 2 : 1;
-    static const int sep_env = [] {
-      const char *e = getenv("PFFT_B200_REG_SEPARATE");
-      return e ? atoi(e) : -1;
-    }();
-    rg.separate = (2 * buf + tab + 1024 <= kSmemLimit / ctas) ? 1 : 0;
-    if (sep_env == 0) rg.separate = 0;
-    if (sep_env == 1 && 2 * buf + tab <= kSmemLimit) rg.separate = 1;
-    break;
+    tl = tl > 2 ? tl - (tl > 8 ? 4 : (tl > 4 ? 2 : 1)) : 1;
   }
   sp.tl = tl;
-  sp.line_bars = 1;
+  static const int line_bars = [] {
+    const char *e = getenv("PFFT_B200_REG_LINEBAR");
+    return e ? atoi(e) : 1;
+  }();
+  sp.line_bars = line_bars;
+  // simple sides: one chunk, window starting at index 0 (the kernel checks the count), no modulation on the store
+  const bool one_in_chunk = g.iseg_stride == 0 || g.iblk >= g.nin;
+  rg.simple_in = (one_in_chunk && g.zin == 0) ? 1 : 0;
+  rg.simple_out = (g.noseg == 1 && g.zout == 0 && !g.mod_out.on && !g.conj_out) ? 1 : 0;
   rg.diblk = make_fastdiv((unsigned)std::max(1, sp.iblk));
   rg.doblk = make_fastdiv((unsigned)std::max(1, sp.oblk));
   // ---- tables: [pass 2 | pass 3 of the sub-transform | w_NL^m | w_n^k], rounded once from fp64 roots
@@ -152,8 +176,7 @@ bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, st
   {
     std::vector<double> roots(2 * (size_t)nsub), pp;
     make_twiddles_f64(nsub, roots.data());
-    size_t off2 = 0, off3 = 0;
-    pow2_twiddle_tables(nsub, roots.data(), &pp, &off2, &off3);
+    reg_pass_tables(nsub, E, roots.data(), &pp);
     all.insert(all.end(), pp.begin(), pp.end());
   }
   if (Q > 1) {

@@ -62,7 +62,10 @@ struct RegParams {
   int NL;                    // complex points per line: n, or n / 2 for real lines
   int kind;                  // 0 complex, 1 r2c, 2 c2r
   int pitch;                 // complex elements per buffer line
-  int separate;              // inputs are fetched into a buffer of their own (double buffering)
+  int separate;              // inputs are fetched into a buffer of their own (double buffering) ...
+  int spitch;                // ... of dense lines with this pitch
+  int simple_in, simple_out; // one chunk, window starting at 0, no modulation / conjugation on that side's addressing
+  int E, maxt;               // points per thread and thread class the stage was planned for
   FastDiv diblk, doblk;
   const void *tables;        // [pass-2 | pass-3 twiddles of the sub-transform | w_NL^m (Q > 1) | w_n^k, k <= n/2 (real lines)]
 };
