@@ -639,9 +639,40 @@ def main():
             results[mode] = 2 * flops_per_transform(n, real) / te.item() / 1e9
             ha.copy_(a)
         best = max(results, key=results.get)
+        # PCIe ceiling of this box: pinned-memory copies alone and in both directions at once (what bounds e2e)
+        pcie = None
+        try:
+            nb = min(1 << 30, bytes_in)
+            hsrc = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            hdst = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+            dsrc = torch.empty(nb, dtype=torch.uint8, device=dev)
+            ddst = torch.empty(nb, dtype=torch.uint8, device=dev)
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+            def rate(h2d, d2h, reps=3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    if h2d:
+                        with torch.cuda.stream(s1):
+                            ddst.copy_(hsrc, non_blocking=True)
+                    if d2h:
+                        with torch.cuda.stream(s2):
+                            hdst.copy_(dsrc, non_blocking=True)
+                torch.cuda.synchronize()
+                return reps * nb / (time.perf_counter() - t0) / 1e9
+            rate(True, True, 1)
+            pcie = {"h2d_alone_gbs": rate(True, False), "d2h_alone_gbs": rate(False, True),
+                    "both_directions_each_gbs": rate(True, True)}
+            del hsrc, hdst, dsrc, ddst
+        except Exception as ex:
+            pcie = {"error": repr(ex)}
         e2e = {"value": results[best], "unit": "GFlop/s",
                "h2d_bytes_per_step": bytes_in + bytes_mid, "d2h_bytes_per_step": bytes_mid + bytes_in,
                "steps": e_steps, "mode": best, "blocking_gflops": results["blocking"], "async_gflops": results["async"],
+               "pcie_measured": pcie,
+               "pcie_bound_gflops": (2 * flops_per_transform(n, real) / ((bytes_in + bytes_mid) / (pcie["both_directions_each_gbs"] * 1e9)) / 1e9
+                                     if pcie and "both_directions_each_gbs" in pcie else None),
                "note": "per rank bytes; pfft_execute_dft (blocking) / pfftb200_execute_async (stream-ordered, chunked copies "
                        "on both PCIe directions) on pinned host arrays; every step copies input and output of BOTH transforms"}
         del ha, hb
