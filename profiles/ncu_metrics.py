@@ -29,6 +29,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h, units = rows[0], rows[1]
+if "Kernel Name" in h:
+    i = h.index("Kernel Name")
+    for n, r in enumerate(rows[2:]):
+        print("launch %d: %s" % (n, r[i][:150]))
 for w in WANT:
     if w in h:
         i = h.index(w)

@@ -125,6 +125,11 @@ SINGLE_RANK = [
     dict(kind="c2r", n=[4, 4, 3072], np=[1, 1], sign=+1, tag="-reg"),
     dict(kind="r2c", n=[12, 12, 768], ni=[8, 8, 512], no=[12, 12, 768], np=[1, 1], flags=T_OUT, tag="-reg"),       # config 5 in small
     dict(kind="c2r", n=[12, 12, 768], ni=[12, 12, 768], no=[8, 8, 512], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    # long lines of the any-length kernel: large prime (Bluestein through the global workspace), 3 * 4096, prime 6397
+    dict(kind="c2c", n=[4, 4, 8191], np=[1, 1], tag="-long"),
+    dict(kind="c2c", n=[4, 12288, 4], np=[1, 1], flags=T_OUT, tag="-long"),
+    dict(kind="c2c", n=[8, 8, 6397], np=[1, 1], tag="-long"),
+    dict(kind="r2c", n=[4, 4, 8192], np=[1, 1], precision="single", tag="-long"),
     # plane-fused last pair (power-of-two lines of equal length in the last two stages)
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_OUT, tag="-fused"),
     dict(kind="c2c", n=[64, 64, 64], np=[1, 1], flags=T_IN, sign=+1, tag="-fused"),
