@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
   const int tl = sp.tl;
-  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int skew = tl >= 8 ? 1 : 8 / tl;
   const int pitch = N + (N >> 4) + skew;
   const int tid = threadIdx.x;
   // per-pass twiddle tables live in shared memory behind the exchange buffer (persistent CTA:
@@ -76,10 +76,14 @@ __global__ void __launch_bounds__(MAXT, (MAXT <= 256 ? 2 : 1)) stage_pow2_kernel
   // mapping), only those warps need to meet -- named barrier 1 + line -- so the lines of a tile
   // drift apart and their load / butterfly / exchange phases overlap.  Where the store mapping is
   // tile-minor (strided side), the last exchange mixes lines and needs the CTA-wide barrier.
-  const bool lbar_in = sp.line_bars && in_line_major && (THREADS % 32 == 0);
+  // (tiles of more than 15 lines -- 16-line fp32 tiles -- share a named barrier between `bg` neighbouring lines)
+  int bg = 1;
+  while (tl / bg > 15) bg *= 2;
+  const bool lbar_in = sp.line_bars && in_line_major && (THREADS % 32 == 0) && tl % bg == 0;
   const bool lbar_out = lbar_in && out_line_major && sp.line_bars != 2;   // 2: experiment (CTA-wide around the last exchange)
+  const int bar_id = 1 + tt_in / bg, bar_cnt = bg * THREADS;
   auto sync_lines = [&](bool per_line) {
-    if (per_line) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_in), "n"(THREADS) : "memory");
+    if (per_line) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_cnt) : "memory");
     else __syncthreads();
   };
 
@@ -315,7 +319,7 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T> *smem = reinterpret_cast<cx<T> *>(smem_raw);
   const int tl = spA.tl;
-  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int skew = tl >= 8 ? 1 : 8 / tl;
   const int pitch = N + (N >> 4) + skew;
   const int tid = threadIdx.x;
   constexpr int TW2 = (P::R2 - 1) * P::R1;
@@ -335,12 +339,15 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
   // both stages read contiguous lines: load / butterfly mapping is line-major throughout
   const int t_in = tid % THREADS, tt_in = tid / THREADS;
   constexpr bool backward = BWD;
-  const bool per_line = (THREADS % 32 == 0) && tl <= 15;
+  int bg = 1;                       // lines sharing one named barrier (at most 15 groups)
+  while (tl / bg > 15) bg *= 2;
+  const bool per_line = (THREADS % 32 == 0) && tl % bg == 0;
+  const int bar_id = 1 + tt_in / bg, bar_cnt = bg * THREADS;
   cx<T> *const my_line_in = smem + tt_in * pitch;
   const unsigned my_line_in_s = (unsigned)__cvta_generic_to_shared(my_line_in);
   const int pt_in = phys(t_in);
   auto sync_lines = [&](bool pl) {
-    if (pl) asm volatile("bar.sync %0, %1;" ::"r"(1 + tt_in), "n"(THREADS) : "memory");
+    if (pl) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_cnt) : "memory");
     else __syncthreads();
   };
 
@@ -561,7 +568,7 @@ cudaError_t launch_fused_class(StageParams &a, StageParams &b, FusePlanes &fp, c
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const int tl = a.tl;
-  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int skew = tl >= 8 ? 1 : 8 / tl;
   const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
   auto kfwd = fused_pair_kernel<T, N, E, MAXT, false, true>;
   auto kbwd = fused_pair_kernel<T, N, E, MAXT, true, true>;
@@ -939,7 +946,7 @@ template <typename T, int N, int E, int MAXT>
 cudaError_t launch_block_class(StageParams &sp, cudaStream_t stream) {
   constexpr int THREADS = N / E;
   const int tl = sp.tl;
-  const int skew = tl <= 8 ? 8 / tl : 0;
+  const int skew = tl >= 8 ? 1 : 8 / tl;
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
@@ -995,6 +1002,10 @@ template <typename T, int N, int E>
 cudaError_t launch_variant(StageParams &sp, cudaStream_t stream) {
   constexpr int THREADS = N / E;
   if (sp.tl * THREADS <= 256) return launch_block_class<T, N, E, (THREADS > 256 ? THREADS : 256)>(sp, stream);
+  // fp32: 16-line tiles of 1024 threads on 64 registers (128-byte runs on a strided side)
+  if constexpr (sizeof(T) == 4) {
+    if (sp.tl * THREADS > 512) return launch_block_class<T, N, E, 1024>(sp, stream);
+  }
   return launch_block_class<T, N, E, (THREADS > 512 ? THREADS : 512)>(sp, stream);
 }
 
@@ -1046,6 +1057,13 @@ int pow2_pick_tile(const Stage &g, int L) {
   // measured on B200 (1024^3 fp64): 128-byte runs on the strided side beat two resident CTAs
   // (8.4 vs 10.5 ms per pass; 6.8 vs 10.5 ms when half of the stores cross NVLink)
   if (strided && sizeof(T) == 8) block = 512;
+  // fp32: 16 lines of 64 threads = 128-byte runs (PFFT_B200_F32_BLOCK=512 restores the 8-line tiles)
+  static const int f32_block = [] {
+    const char *e = getenv("PFFT_B200_F32_BLOCK");
+    return e ? atoi(e) : 1024;
+  }();
+  const int max_block = sizeof(T) == 4 ? f32_block : 512;
+  if (strided && sizeof(T) == 4 && threads >= 32) block = max_block;
   int tl = block / threads;
   if (forced > 0 && strided) tl = forced;
   static const int forced_c = [] {
@@ -1053,7 +1071,7 @@ int pow2_pick_tile(const Stage &g, int L) {
     return e ? atoi(e) : 0;
   }();
   if (forced_c > 0 && !strided) tl = forced_c;
-  while (tl * threads > 512 && tl > 1) tl /= 2;
+  while (tl * threads > max_block && tl > 1) tl /= 2;
   if (tl < 1) tl = 1;
   if (g.tile_dim < 0) tl = 1;
   else if ((INT)tl > g.batch[g.tile_dim].extent) {
@@ -1139,7 +1157,7 @@ void pow2_prepare(const Stage &g, StageParams &sp) {
     const char *e = getenv("PFFT_B200_LINEBAR");
     return e ? atoi(e) : 1;
   }();
-  sp.line_bars = sp.tl <= 15 ? line_bars : 0;
+  sp.line_bars = line_bars;   // (tiles of more than 15 lines share barriers between neighbouring lines)
   if (!fast) return;
   for (int e = 0; e < E; e++) {
     const long long idx = (long long)e * threads;
