@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(MAXT, 1) stage_reg_kernel(const __grid_constan
       }
       *reinterpret_cast<V *>(reinterpret_cast<cx<T> *>(sp.out[seg]) + line0 + (long long)kl * sp.ostride) = raw;
     };
-    auto store_all = [&](int t_s, int tt_s, cx<T> nyq) {
+    auto store_all = [&](int t_s, int tt_s) {
       if (tt_s >= tvalid_cur) return;
       const long long line0 = obase_cur + (long long)tt_s * t_os;
       if (simple_out) {
@@ -345,20 +345,13 @@ __global__ void __launch_bounds__(MAXT, 1) stage_reg_kernel(const __grid_constan
           raw.y = BWD ? x[e].x : x[e].y;
           *reinterpret_cast<V *>(out + e * out_step) = raw;
         }
-        if (KIND == 1 && t_s == 0 && NL < sp.nout) {
-          V raw;
-          raw.x = nyq.x;
-          raw.y = nyq.y;
-          *reinterpret_cast<V *>(out + E * out_step) = raw;
-        }
       } else {
 #pragma unroll
         for (int e = 0; e < E; e++) store(t_s + e * TL, x[e], line0);
-        if (KIND == 1 && t_s == 0) store(NL, nyq, line0);
       }
     };
     if (regs_out) {
-      store_all(r_c, tt_c, cx<T>{(T)0, (T)0});
+      store_all(r_c, tt_c);
       continue;
     }
     // ---- last exchange: natural order, dense, into the line (plus Z[0] once more behind it, so that the mirror
@@ -370,26 +363,69 @@ __global__ void __launch_bounds__(MAXT, 1) stage_reg_kernel(const __grid_constan
       if (KIND == 1 && r_c == 0) line_w[NL] = x[0];
     }
     sync_lines(lbar_out);
-    cx<T> nyq{(T)0, (T)0};
+    const cx<T> *line_r = xbuf + tt_out * pitch;
+    if (KIND == 0) {
+#pragma unroll
+      for (int e = 0; e < E; e++) x[e] = line_r[t_out + e * TL];
+      sync_lines(lbar_out);                    // everybody has read the lines: the next tile may scatter into them
+      store_all(t_out, tt_out);
+      continue;
+    }
+    // ---- r2c post-processing by pairs (k, M - k), M = NL, k = t_out + e TL < M / 2:
+    //   E = (Z[k] + conj Z[M-k]) / 2,  P = w^k (Z[k] - conj Z[M-k]) / (2i):   X[k] = E + P,  X[M-k] = conj(E - P)
+    // (k = 0 yields the DC and the Nyquist bin; the middle bin X[M/2] = conj Z[M/2] is one extra element)
+    cx<T> mid{(T)0, (T)0};
     {
-      const cx<T> *line_r = xbuf + tt_out * pitch;
-      if (KIND == 0) {
+      const cx<T> *za = line_r + t_out, *zb = line_r + (NL - t_out), *wk = twh + t_out;
 #pragma unroll
-        for (int e = 0; e < E; e++) x[e] = line_r[t_out + e * TL];
-      } else {
-        // r2c post-processing, M = NL: X[k] = E + w^k O,  E = (Z[k] + conj Z[M-k]) / 2,  O = (Z[k] - conj Z[M-k]) / (2i)
-        const cx<T> *za = line_r + t_out, *zb = line_r + (NL - t_out), *wk = twh + t_out;
-        auto post = [&](cx<T> a, cx<T> b, cx<T> w) -> cx<T> {
-          const cx<T> Ee{(T)0.5 * (a.x + b.x), (T)0.5 * (a.y - b.y)}, D{(T)0.5 * (a.x - b.x), (T)0.5 * (a.y + b.y)};
-          return cx<T>{Ee.x + D.y * w.x + D.x * w.y, Ee.y + D.y * w.y - D.x * w.x};      // E + (D / i) w
-        };
-#pragma unroll
-        for (int e = 0; e < E; e++) x[e] = post(za[e * TL], zb[-e * TL], wk[e * TL]);
-        if (t_out == 0) nyq = post(line_r[NL], line_r[0], twh[NL]);
+      for (int e = 0; e < E / 2; e++) {
+        const cx<T> a = za[e * TL], b = zb[-e * TL], w = wk[e * TL];
+        const cx<T> Ee{(T)0.5 * (a.x + b.x), (T)0.5 * (a.y - b.y)}, D{(T)0.5 * (a.x - b.x), (T)0.5 * (a.y + b.y)};
+        const cx<T> Pp{D.y * w.x + D.x * w.y, D.y * w.y - D.x * w.x};       // (D / i) w
+        x[e] = cx<T>{Ee.x + Pp.x, Ee.y + Pp.y};
+        x[E / 2 + e] = cx<T>{Ee.x - Pp.x, Pp.y - Ee.y};
+      }
+      if (t_out == 0) {
+        const cx<T> m = line_r[NL / 2];
+        mid = cx<T>{m.x, -m.y};
       }
     }
     sync_lines(lbar_out);                      // everybody has read the lines: the next tile may scatter into them
-    store_all(t_out, tt_out, nyq);
+    if (tt_out < tvalid_cur) {
+      const long long line0 = obase_cur + (long long)tt_out * t_os;
+      if (simple_out) {
+        cx<T> *const base = reinterpret_cast<cx<T> *>(sp.out[0]) + line0;
+        cx<T> *lo = base + out_first, *hi = base + (long long)NL * sp.ostride - out_first;
+#pragma unroll
+        for (int e = 0; e < E / 2; e++) {
+          const int k = t_out + e * TL;
+          V raw;
+          if (k < sp.nout) {
+            raw.x = x[e].x;
+            raw.y = x[e].y;
+            *reinterpret_cast<V *>(lo + e * out_step) = raw;
+          }
+          if (NL - k < sp.nout) {
+            raw.x = x[E / 2 + e].x;
+            raw.y = x[E / 2 + e].y;
+            *reinterpret_cast<V *>(hi - e * out_step) = raw;
+          }
+        }
+        if (t_out == 0 && NL / 2 < sp.nout) {
+          V raw;
+          raw.x = mid.x;
+          raw.y = mid.y;
+          *reinterpret_cast<V *>(base + (long long)(NL / 2) * sp.ostride) = raw;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < E / 2; e++) {
+          store(t_out + e * TL, x[e], line0);
+          store(NL - t_out - e * TL, x[E / 2 + e], line0);
+        }
+        if (t_out == 0) store(NL / 2, mid, line0);
+      }
+    }
   }
 }
 
