@@ -86,10 +86,21 @@ static bool all_ranks_ok(MPI_Comm comm, bool ok) {
   return all != 0;
 }
 
+// Planning-time device allocations: a failure (out of memory) makes the planner return NULL with
+// pfftb200_last_error set, like the reference's planners (kernel/partrafo.c:337-373), instead of aborting.
+static bool try_malloc(void **p, size_t bytes, std::string *err) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaSuccess) return true;
+  cudaGetLastError();
+  *p = nullptr;
+  if (err && err->empty()) *err = "cudaMalloc(" + std::to_string(bytes) + " bytes) failed: " + cudaGetErrorString(e);
+  return false;
+}
+
 static void *upload_device(const void *host, size_t bytes, void *ctx) {
   PlanBase *pl = static_cast<PlanBase *>(ctx);
   void *dev = nullptr;
-  CUDA_OK(cudaMalloc(&dev, bytes));
+  CUDA_OK(cudaMalloc(&dev, bytes));      // (twiddle tables: kilobytes)
   CUDA_OK(cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice));
   pl->tables.push_back(dev);
   return dev;
@@ -408,11 +419,18 @@ PlanBase *plan_create(int prec, const Problem &p, void *in, void *out, MPI_Comm 
   // plans with real exchanges own their receive areas from the start (peers map them);
   // purely local plans borrow user buffers where they can and allocate scratch lazily
   if (any_exchange) {
-    if (nst >= 2) CUDA_OK(cudaMalloc(&pl->scratch[0], pl->scratch_bytes));
-    if (nst >= 3) CUDA_OK(cudaMalloc(&pl->scratch[1], pl->scratch_bytes));
-    if (tr == TR_NCCL) CUDA_OK(cudaMalloc(&pl->scratch[2], pl->scratch_bytes));
+    std::string aerr;
+    bool aok = true;
+    if (nst >= 2) aok = try_malloc(&pl->scratch[0], pl->scratch_bytes, &aerr) && aok;
+    if (nst >= 3) aok = try_malloc(&pl->scratch[1], pl->scratch_bytes, &aerr) && aok;
+    if (tr == TR_NCCL) aok = try_malloc(&pl->scratch[2], pl->scratch_bytes, &aerr) && aok;
     pl->scratch_cap[0] = pl->scratch[0] ? pl->scratch_bytes : 0;
     pl->scratch_cap[1] = pl->scratch[1] ? pl->scratch_bytes : 0;
+    if (!all_ranks_ok(pl->comm_cart, aok)) {
+      set_error(aerr.empty() ? "receive areas could not be allocated on another rank" : aerr);
+      plan_destroy(pl);
+      return nullptr;
+    }
   }
   if (any_exchange) {
     std::string terr;
