@@ -186,8 +186,28 @@ def nvlink_counters(index):
                     tx += kib * 1024
                 else:
                     rx += kib * 1024
-        return (tx, rx) if seen else None
+        if seen:
+            return (tx, rx)
     except Exception:
+        pass
+    # NVML field values: data throughput counters in KiB, summed over all links (scope id = all links)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)
+        if os.environ.get("PFFT_BENCH_DEBUG"):
+            sys.stderr.write("nvml nvlink throughput counters (bytes): %r\n" % (out,))
+        return tuple(out)
+    except Exception as ex:
+        if os.environ.get("PFFT_BENCH_DEBUG"):
+            sys.stderr.write("nvml nvlink counters failed: %r\n" % (ex,))
         return None
 
 
@@ -594,7 +614,7 @@ def main():
         combined["nvlink_counters_rank0"] = {"tx_bytes_per_step": (nvl1[0] - nvl0[0]) / args.steps,
                                              "rx_bytes_per_step": (nvl1[1] - nvl0[1]) / args.steps,
                                              "algorithmic_bytes_per_step_each_way": 2 * nvl_bytes,
-                                             "source": "nvidia-smi nvlink -gt d, all links of GPU %d" % local_rank}
+                                             "source": "NVLink data throughput counters (nvidia-smi nvlink -gt d / NVML field values), all links of GPU %d" % local_rank}
     for tag, pk in (("measured", NVLINK_MEASURED), ("nominal", NVLINK_NOMINAL)):
         t_nvl = nvl_bytes / (pk * 1e9) * 1e3
         combined[tag] = {"nvlink_peak_gbs": pk, "t_nvlink_ms": t_nvl, "t_roof_serial_ms": t_hbm + t_nvl,

@@ -169,6 +169,10 @@ bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, st
   const bool one_in_chunk = g.iseg_stride == 0 || g.iblk >= g.nin;
   rg.simple_in = (one_in_chunk && g.zin == 0) ? 1 : 0;
   rg.simple_out = (g.noseg == 1 && g.zout == 0 && !g.mod_out.on && !g.conj_out) ? 1 : 0;
+  {
+    const long long present = rg.kind == 1 ? (g.zin + g.nin) / 2 : g.zin + g.nin;      // packed / complex points up to the end of the window
+    rg.third_zero = (Q == 3 && rg.kind != 2 && present <= 2ll * nsub) ? 1 : 0;
+  }
   rg.diblk = make_fastdiv((unsigned)std::max(1, sp.iblk));
   rg.doblk = make_fastdiv((unsigned)std::max(1, sp.oblk));
   // ---- tables: [pass 2 | pass 3 of the sub-transform | w_NL^m | w_n^k], rounded once from fp64 roots

@@ -66,6 +66,7 @@ struct RegParams {
   int spitch;                // ... of dense lines with this pitch
   int simple_in, simple_out; // one chunk, window starting at 0, no modulation / conjugation on that side's addressing
   int E, maxt;               // points per thread and thread class the stage was planned for
+  int third_zero;            // Q = 3: the last third of every input line is zero padding
   FastDiv diblk, doblk;
   const void *tables;        // [pass-2 | pass-3 twiddles of the sub-transform | w_NL^m (Q > 1) | w_n^k, k <= n/2 (real lines)]
 };

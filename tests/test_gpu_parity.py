@@ -108,6 +108,10 @@ SINGLE_RANK = [
     dict(kind="r2c", n=[8, 16, 256], ni=[8, 16, 128], no=[8, 16, 256], np=[1, 1], flags=T_OUT, tag="-reg"),
     dict(kind="c2r", n=[8, 16, 256], ni=[8, 16, 256], no=[8, 16, 128], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
     dict(kind="r2c", n=[8, 16, 256], ni=[8, 16, 128], no=[8, 16, 256], np=[1, 1], flags=S_IN | S_OUT, tag="-reg"),
+    dict(kind="r2c", n=[8, 16, 256], ni=[8, 16, 256], no=[4, 8, 128], np=[1, 1], flags=T_OUT, tag="-reg"),      # truncated half spectrum (upper end kept)
+    dict(kind="c2r", n=[8, 16, 256], ni=[4, 8, 128], no=[8, 16, 256], np=[1, 1], flags=T_IN, sign=+1, tag="-reg"),
+    dict(kind="r2c", n=[8, 16, 768], ni=[8, 16, 768], no=[4, 8, 384], np=[1, 1], tag="-reg"),
+    dict(kind="c2r", n=[8, 16, 768], ni=[4, 8, 384], no=[8, 16, 768], np=[1, 1], sign=+1, precision="single", tag="-reg"),
     dict(kind="c2c", n=[4, 8, 768], np=[1, 1], tag="-reg"),
     dict(kind="c2c", n=[4, 8, 768], np=[1, 1], sign=+1, flags=T_OUT, tag="-reg"),
     dict(kind="c2c", n=[768, 4, 8], np=[1, 1], flags=T_OUT, tag="-reg"),
