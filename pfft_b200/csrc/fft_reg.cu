@@ -67,12 +67,6 @@ void reg_pass_tables(int L, int E, const double *roots, std::vector<double> *tab
   if (R3 > 1) emit(R1 * R2, R3);
 }
 
-int floor_pow2_int(long long x) {
-  int p = 1;
-  while ((long long)p * 2 <= x) p *= 2;
-  return p;
-}
-
 int kind_of(const Stage &g) { return g.op == OP_R2C ? 1 : (g.op == OP_C2R ? 2 : 0); }
 
 }  // namespace

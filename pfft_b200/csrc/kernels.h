@@ -62,8 +62,7 @@ struct RegParams {
   int NL;                    // complex points per line: n, or n / 2 for real lines
   int kind;                  // 0 complex, 1 r2c, 2 c2r
   int pitch;                 // complex elements per buffer line
-  int separate;              // inputs are fetched into a buffer of their own (double buffering) ...
-  int spitch;                // ... of dense lines with this pitch
+  int spitch;                // pitch of the staging buffer's dense lines (inputs are fetched into a buffer of their own)
   int simple_in, simple_out; // one chunk, window starting at 0, no modulation / conjugation on that side's addressing
   int E, maxt;               // points per thread and thread class the stage was planned for
   int third_zero;            // Q = 3: the last third of every input line is zero padding
