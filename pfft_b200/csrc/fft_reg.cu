@@ -200,6 +200,8 @@ template <typename T>
 cudaError_t launch_stage_reg(StageParams &sp, cudaStream_t stream) {
   if (sp.ntiles <= 0) return cudaSuccess;
   if (sp.ntiles >= (1ll << 31)) return cudaErrorInvalidValue;
+  sp.rg.dalong = make_fastdiv((unsigned)std::max<long long>(1, sp.tiles_along));
+  for (int k = 0; k < kMaxBatch; k++) sp.rg.dbext[k] = make_fastdiv((unsigned)std::max<long long>(1, k < sp.nbatch ? sp.bext[k] : 1));
   const bool f64 = sizeof(T) == 8;
   switch (sp.rg.kind) {
     case 0: return f64 ? launch_reg_k0_f64(sp, stream) : launch_reg_k0_f32(sp, stream);

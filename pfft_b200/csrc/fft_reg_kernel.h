@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(MAXT, 1) stage_reg_kernel(const __grid_constan
     obase = 0;
     tvalid = 1;
     if (sp.tile_dim >= 0) {
+      // (divisions by run-time extents through host-made magic numbers: a few instructions instead of ~25 each)
       const unsigned along = (unsigned)sp.tiles_along;
-      const unsigned chunk = rest % along;
-      rest /= along;
+      const unsigned qa = rg_div(rest, sp.rg.dalong);
+      const unsigned chunk = rest - qa * along;
+      rest = qa;
       const long long first = (long long)chunk * tl;
       const long long left = sp.bext[sp.tile_dim] - first;
       tvalid = left < tl ? (int)left : tl;
@@ -115,8 +117,9 @@ __global__ void __launch_bounds__(MAXT, 1) stage_reg_kernel(const __grid_constan
     for (int k = kMaxBatch - 1; k >= 0; k--) {
       if (k >= sp.nbatch || k == sp.tile_dim) continue;
       const unsigned ext = (unsigned)sp.bext[k];
-      const unsigned c = rest % ext;
-      rest /= ext;
+      const unsigned qe = rg_div(rest, sp.rg.dbext[k]);
+      const unsigned c = rest - qe * ext;
+      rest = qe;
       ibase += (long long)c * sp.bis[k];
       obase += (long long)c * sp.bos[k];
     }

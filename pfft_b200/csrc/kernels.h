@@ -67,6 +67,7 @@ struct RegParams {
   int E, maxt;               // points per thread and thread class the stage was planned for
   int third_zero;            // Q = 3: the last third of every input line is zero padding
   FastDiv diblk, doblk;
+  FastDiv dalong, dbext[kMaxBatch];   // tile walk: tiles along the tile dimension, batch extents (filled at launch)
   const void *tables;        // [pass-2 | pass-3 twiddles of the sub-transform | w_NL^m (Q > 1) | w_n^k, k <= n/2 (real lines)]
 };
 
