@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <type_traits>
 #include <vector>
 
@@ -405,8 +406,9 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
       unsigned chunk = rest;
       if (!FUSED || sp.nbatch > 2) {
         const unsigned along = (unsigned)sp.tiles_along;
-        chunk = rest % along;
-        rest /= along;
+        const unsigned qa = fast_div(rest, sp.rg.dalong.m, sp.rg.dalong.s1, sp.rg.dalong.s2);   // (host-made magic numbers)
+        chunk = rest - qa * along;
+        rest = qa;
       }
       const long long first = (long long)chunk * tl;
       const long long left = sp.bext[sp.tile_dim] - first;
@@ -419,8 +421,9 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
       for (int k = kMaxBatch - 1; k >= (FUSED ? 1 : 0); k--) {
         if (k >= sp.nbatch || k == sp.tile_dim) continue;
         const unsigned ext = (unsigned)sp.bext[k];
-        const unsigned c = rest % ext;
-        rest /= ext;
+        const unsigned qe = fast_div(rest, sp.rg.dbext[k].m, sp.rg.dbext[k].s1, sp.rg.dbext[k].s2);
+        const unsigned c = rest - qe * ext;
+        rest = qe;
         ibase += (long long)c * sp.bis[k];
         obase += (long long)c * sp.bos[k];
       }
@@ -562,8 +565,16 @@ fused_pair_kernel(const __grid_constant__ StageParams spA, const __grid_constant
   publish();
 }
 
+// magic numbers of the divisions in the kernels' tile walk (tiles along the tile dimension, batch extents)
+void fill_walk_divisors(StageParams &sp) {
+  sp.rg.dalong = make_fastdiv((unsigned)std::max<long long>(1, sp.tiles_along));
+  for (int k = 0; k < kMaxBatch; k++) sp.rg.dbext[k] = make_fastdiv((unsigned)std::max<long long>(1, k < sp.nbatch ? sp.bext[k] : 1));
+}
+
 template <typename T, int N, int E, int MAXT>
 cudaError_t launch_fused_class(StageParams &a, StageParams &b, FusePlanes &fp, cudaStream_t stream) {
+  fill_walk_divisors(a);
+  fill_walk_divisors(b);
   constexpr int THREADS = N / E;
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
@@ -809,8 +820,9 @@ __global__ void __launch_bounds__(MAXT, 1) stage_blk_kernel(const __grid_constan
     for (int k = kMaxBatch - 1; k >= 0; k--) {
       if (k >= sp.nbatch) continue;
       const unsigned ext = (unsigned)sp.bext[k];
-      const unsigned c = rest % ext;
-      rest /= ext;
+      const unsigned qe = fast_div(rest, sp.rg.dbext[k].m, sp.rg.dbext[k].s1, sp.rg.dbext[k].s2);   // (host-made magic numbers)
+      const unsigned c = rest - qe * ext;
+      rest = qe;
       ibase += (long long)c * sp.bis[k];
       obase += (long long)c * sp.bos[k];
       if (k == sp.oswz_batch) cswz = c;
@@ -903,6 +915,7 @@ cudaError_t launch_blk_class(StageParams &sp, cudaStream_t stream) {
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const int tl = sp.tl;
+  fill_walk_divisors(sp);
   const StageGeom sg = stage_geom(N, tl, sp.iblk2, sp.iblk, sp.iseg_stride, 2 * (int)sizeof(T));
   // half-CTA tile-minor exchange: opt-in (PFFT_B200_HALFCTA=1), 512-thread tiles of 8 lines, blocked output,
   // every chunk local (64-byte stores over NVLink reach 477 GB/s against 707 GB/s for 128 bytes and more)
@@ -950,6 +963,7 @@ cudaError_t launch_block_class(StageParams &sp, cudaStream_t stream) {
   using P = Passes<N, E>;
   constexpr int TWN = (P::R2 - 1) * P::R1 + (P::NPASS == 3 ? (P::R3 - 1) * P::R1 * P::R2 : 0);
   const size_t smem = ((size_t)tl * (N + (N >> 4) + skew) + TWN) * 2 * sizeof(T);
+  fill_walk_divisors(sp);
   if (sp.fast && sp.istride == 1) {
     // contiguous input lines: the lean body shared with the plane-fused pair
     auto kf = fused_pair_kernel<T, N, E, MAXT, false, false>;
