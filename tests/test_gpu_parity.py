@@ -423,3 +423,45 @@ def test_baseline_configs_round_trip_at_full_size(built_lib, cfg):
         # reduce is the adjoint of exchange: what all ghost-cell blocks held is what the owners hold afterwards
         ex, red = sum(r["gc"]["exchanged_sum"] for r in res), sum(r["gc"]["reduced_sum"] for r in res)
         assert abs(ex - red) <= 1e-12 * abs(ex), (ex, red)
+
+
+def test_execute_async_is_graph_capturable(world):
+    """A stream-ordered execute (pfftb200_execute_async on device arrays) contains nothing but kernel launches with
+    static parameters: captured once into a CUDA graph on the plan's stream and replayed on new data, it must
+    reproduce the transform.  (Launch-bound small transforms are what graphs are for: 64^3 is three ~10 us kernels.)"""
+    import torch
+    pf = world
+    n = [64, 64, 64]
+    N = int(np.prod(n))
+    comm = pf.create_procmesh([1, 1])
+    side = torch.cuda.Stream()
+    pf.set_stream(side.cuda_stream)
+    try:
+        x = torch.zeros(N, 2, dtype=torch.float64, device="cuda")
+        X = torch.zeros_like(x)
+        plan = pf.plan_dft(n, x, X, comm, pf.FORWARD, T_OUT, dtype=np.complex128)
+        assert plan is not None, pf.last_error()
+        plan.enable_stage_timing(False)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        with torch.cuda.stream(side):
+            x.copy_(torch.rand(N, 2, dtype=torch.float64, device="cuda", generator=g))
+            plan.execute_async(x, X)                      # warm-up: buffers and kernel attributes are set up here
+        side.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            plan.execute_async(x, X)
+        for seed in (5, 6):
+            fresh = torch.rand(N, 2, dtype=torch.float64, device="cuda", generator=g.manual_seed(seed))
+            x.copy_(fresh)
+            X.zero_()
+            torch.cuda.synchronize()
+            graph.replay()
+            torch.cuda.synchronize()
+            want = torch.fft.fftn(torch.view_as_complex(fresh).reshape(n)).permute(1, 2, 0).contiguous()
+            got = torch.view_as_complex(X).reshape(n[1], n[2], n[0])
+            err = ((got - want).abs().max() / want.abs().max()).item()
+            assert err < 1e-12, err
+        plan.destroy()
+    finally:
+        pf.set_stream(0)
+        comm.free()
