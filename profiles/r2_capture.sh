@@ -19,7 +19,8 @@ cap() {  # name, kernel regex, count, command...
 }
 cap blk_c1 "stage_blk" 3 python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --no-spot
 cap c3 "stage_reg|fused_pair" 6 python bench.py --config 3 --steps 1 --warmup 0 --no-cpu --no-e2e --no-spot
-cap c5 "stage_reg|gc_" 10 python bench.py --config 5 --steps 1 --warmup 0 --no-cpu --no-e2e --no-spot
+cap c5 "stage_reg" 6 python bench.py --config 5 --steps 1 --warmup 0 --no-cpu --no-e2e --no-spot
+cap gc "gc_" 4 python bench.py --config 5 --steps 1 --warmup 0 --no-cpu --no-e2e --no-spot
 cap mixed "stage_mixed|stage_generic" 3 python -c "
 import sys; sys.path[:0]=['tests','oracle','.']
 import pfft_b200 as pf, gpu_worker
