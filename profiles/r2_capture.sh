@@ -9,7 +9,7 @@
 mkdir -p gpurun_out
 R=/tmp/ncu_reps; mkdir -p $R
 N="ncu --clock-control none"
-timeout 300 $N --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/p2_launches_bench_n1.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/p2_launches.log 2>&1
+timeout 300 $N --metrics gpu__time_duration.sum -k "regex:stage_|fused_pair|gc_|xch_" -c 400 --csv --log-file gpurun_out/p2_launches_bench_n1.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-spot > gpurun_out/p2_launches.log 2>&1   # (library kernels only: the input generation alone is thousands of torch launches)
 python profiles/summarize_launches.py gpurun_out/p2_launches_bench_n1.csv > gpurun_out/p2_launches_bench_n1.txt 2>&1
 cap() {  # name, kernel regex, count, command...
   name=$1; rx=$2; cnt=$3; shift 3
