@@ -77,6 +77,13 @@ int pfftb200_emulate_stage(int prec, int kind, int rnk_n, const ptrdiff_t *n, co
                            const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
                            unsigned pfft_flags, int stage, const void *in, void *const *outs);
 
+/* Introspection without a device: the kernel family ("pow2" | "reg" | "mixed") and tile geometry the planner picks
+ * for every stage of rank `pid` (JSON list, same calling convention as pfftb200_describe_schedule). */
+size_t pfftb200_describe_kernels(int prec, int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                                 ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                                 const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                                 unsigned pfft_flags, char *buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,9 +76,69 @@ int emulate_stage(const Stage &g, const void *in, void *const *outs) {
   emulate_stage_mixed<T>(sp);
   return 0;
 }
+// which kernel would run stage g, and with what tile geometry (host planning only, no device)
+template <typename T>
+std::string describe_stage_kernel(const Stage &g) {
+  StageParams sp;
+  std::string err;
+  HostTables tabs;
+  if (!stage_params_basic(g, sp, &err)) return "{\"error\":\"" + err + "\"}";
+  const int fam = stage_kernel_family<T>(g, sp.L);
+  const size_t csize = 2 * sizeof(T);
+  std::string j = "{";
+  if (fam == 1) {
+    const int tl = pow2_pick_tile<T>(g, sp.L);
+    const int threads = tl * pow2_threads_per_line(sp.L);
+    j += "\"family\":\"pow2\",\"tl\":" + std::to_string(tl) + ",\"threads\":" + std::to_string(threads) +
+         ",\"micro_blocked\":" + std::to_string(g.ntile > 0 ? 1 : 0);
+  } else if (fam == 3) {
+    if (!reg_prepare<T>(g, sp, upload_host, &tabs, &err)) return "{\"error\":\"" + err + "\"}";
+    const RegParams &rg = sp.rg;
+    const int TL = rg.NL / rg.E;
+    const size_t smem = ((size_t)sp.tl * (rg.pitch + rg.spitch) + rg.table_elems) * csize;
+    j += "\"family\":\"reg\",\"tl\":" + std::to_string(sp.tl) + ",\"threads\":" + std::to_string(sp.tl * TL) +
+         ",\"class_threads\":" + std::to_string(rg.maxt) + ",\"points_per_thread\":" + std::to_string(rg.E) +
+         ",\"complex_points\":" + std::to_string(rg.NL) + ",\"kind\":" + std::to_string(rg.kind) +
+         ",\"smem_bytes\":" + std::to_string(smem) + ",\"simple_in\":" + std::to_string(rg.simple_in) +
+         ",\"simple_out\":" + std::to_string(rg.simple_out) + ",\"third_zero\":" + std::to_string(rg.third_zero);
+  } else {
+    if (g.op == OP_R2R) sp.tw_r2r = make_r2r_table<T>(sp.r2r_D, upload_host, &tabs);
+    if (!mixed_prepare<T>(g, sp, upload_host, &tabs, &err)) return "{\"error\":\"" + err + "\"}";
+    j += "\"family\":\"mixed\",\"tl\":" + std::to_string(sp.tl) + ",\"complex_points\":" + std::to_string(sp.mx.L) +
+         ",\"transform_length\":" + std::to_string(sp.mx.Lc) + ",\"bluestein\":" + std::to_string(sp.mx.bluestein) +
+         ",\"half_real\":" + std::to_string(sp.mx.half_real) + ",\"global_workspace\":" + std::to_string(sp.mx.gws) +
+         ",\"smem_bytes\":" + std::to_string((size_t)sp.tl * sp.mx.pitch * csize) + ",\"passes\":" + std::to_string(sp.mx.npass);
+  }
+  return j + "}";
+}
 }  // namespace
 
 extern "C" {
+
+// TEST SUPPORT / introspection without a device: the kernel family and tile geometry the planner would pick for
+// every stage of rank `pid` (JSON list).  prec 0: fp64, 1: fp32.
+size_t pfftb200_describe_kernels(int prec, int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                                 ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                                 const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                                 unsigned pfft_flags, char *buf, size_t buflen) {
+  Problem p;
+  fill_problem(&p, kind, rnk_n, n, ni, no, howmany, iblock, oblock, rnk_pm, np, sign, kinds, skip_trafos, pfft_flags);
+  Schedule s;
+  std::string j = "[";
+  if (!build_schedule(p, pid, &s)) {
+    j = "{\"error\":\"" + s.error + "\"}";
+  } else {
+    for (size_t i = 0; i < s.stages.size(); i++)
+      j += (i ? "," : "") + (prec == 0 ? describe_stage_kernel<double>(s.stages[i]) : describe_stage_kernel<float>(s.stages[i]));
+    j += "]";
+  }
+  if (buf && buflen) {
+    size_t k = j.size() < buflen - 1 ? j.size() : buflen - 1;
+    memcpy(buf, j.data(), k);
+    buf[k] = 0;
+  }
+  return j.size() + 1;
+}
 
 const char *pfftb200_version(void) { return "pfft_b200 0.1 (sm_100a)"; }
 

@@ -192,6 +192,7 @@ bool reg_prepare(const Stage &g, StageParams &sp, UploadFn upload, void *ctx, st
     return false;
   }
   std::vector<T> host(all.begin(), all.end());
+  rg.table_elems = twn;
   rg.tables = upload(host.data(), host.size() * sizeof(T), ctx);
   return true;
 }

@@ -69,6 +69,7 @@ struct RegParams {
   FastDiv diblk, doblk;
   FastDiv dalong, dbext[kMaxBatch];   // tile walk: tiles along the tile dimension, batch extents (filled at launch)
   const void *tables;        // [pass-2 | pass-3 twiddles of the sub-transform | w_NL^m (Q > 1) | w_n^k, k <= n/2 (real lines)]
+  int table_elems;           // complex entries of `tables` (host bookkeeping: shared-memory footprint)
 };
 
 // Plain-old-data copy of a Stage plus pointers; passed to kernels by value.
@@ -180,5 +181,13 @@ template <typename T>
 cudaError_t launch_stage_reg(StageParams &sp, cudaStream_t stream);
 
 unsigned long long &launch_counter();
+
+// Kernel family of a stage (plan.cu: KernelKind values): 1 pow2 (fft_pow2.cu), 3 reg (fft_reg.cu), 2 mixed (fft_mixed.cu)
+template <typename T>
+inline int stage_kernel_family(const Stage &g, int L) {
+  if (pow2_supported<T>(g, L)) return 1;
+  if (reg_supported<T>(g, L)) return 3;
+  return 2;
+}
 
 }  // namespace pfb

@@ -141,9 +141,9 @@ static bool build_stage_params(PlanBase *pl, std::string *err) {
     StageParams sp;
     if (!stage_params_basic(g, sp, err)) return false;
     const int L = sp.L;
-    const bool fast = pow2_supported<T>(g, L);
-    int kind = fast ? KERNEL_POW2 : (old_generic ? KERNEL_GENERIC : KERNEL_MIXED);
-    if (kind == KERNEL_MIXED && reg_supported<T>(g, L)) kind = KERNEL_REG;
+    int kind = stage_kernel_family<T>(g, L);       // KERNEL_POW2 / KERNEL_REG / KERNEL_MIXED
+    const bool fast = kind == KERNEL_POW2;
+    if (kind == KERNEL_MIXED && old_generic) kind = KERNEL_GENERIC;
     if (g.op == OP_R2R) {
       auto jt = table_of.find(-8 * sp.r2r_D);
       if (jt == table_of.end()) jt = table_of.emplace(-8 * sp.r2r_D, TableSet{make_r2r_table<T>(sp.r2r_D, upload_device, pl), 0, 0}).first;
