@@ -84,6 +84,13 @@ size_t pfftb200_describe_kernels(int prec, int kind, int rnk_n, const ptrdiff_t 
                                  const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
                                  unsigned pfft_flags, char *buf, size_t buflen);
 
+/* Introspection without a device: the device-side ordering of the p2p transport for rank `pid` (JSON: per boundary
+ * remote / receive area / storing ranks, per stage the [rank, previous-execute, stages-completed] triples it waits for). */
+size_t pfftb200_describe_exchange_ordering(int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                                           ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                                           const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                                           unsigned pfft_flags, char *buf, size_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

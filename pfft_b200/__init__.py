@@ -366,6 +366,22 @@ def describe_kernels(kind, n, np_, pid, flags=0, ni=None, no=None, howmany=1, ib
     return json.loads(buf.value.decode())
 
 
+def describe_exchange_ordering(kind, n, np_, pid, flags=0, ni=None, no=None, howmany=1, iblock=None, oblock=None, sign=-1,
+                               kinds=None, skip=None):
+    """Device-side ordering of the p2p transport for rank `pid`, without MPI/CUDA (pfftb200_describe_exchange_ordering)."""
+    d = len(n)
+    fn = lib().pfftb200_describe_exchange_ordering
+    fn.restype = C.c_size_t
+    args = [C.c_int({"c2c": 0, "r2c": 1, "c2r": 2, "r2r": 3}[kind]), C.c_int(d), _vec(n),
+            _vec(ni if ni is not None else n), _vec(no if no is not None else n), INT(howmany), _vec(iblock),
+            _vec(oblock), C.c_int(len(np_)), _vec(np_, C.c_int), C.c_int(pid), C.c_int(sign), _vec(kinds, C.c_int),
+            _vec(skip, C.c_int), C.c_uint(flags)]
+    need = fn(*args, None, C.c_size_t(0))
+    buf = C.create_string_buffer(need + 8)
+    fn(*args, buf, C.c_size_t(need + 8))
+    return json.loads(buf.value.decode())
+
+
 def launch_count():
     f = lib().pfftb200_launch_count
     f.restype = C.c_ulonglong

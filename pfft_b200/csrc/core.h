@@ -169,6 +169,23 @@ struct Schedule {
   std::string error;            // non-empty: unsupported configuration
 };
 
+// Device-side ordering of the p2p transport (transports.cu) as a pure function of the schedule: what stage `stage`
+// must wait for before it may run.  Every rank publishes its progress (64 * execute + stages completed) to its peers;
+//  (a) a stage whose input was stored by the members of an exchange group waits until all of them have completed
+//      the stage before;
+//  (b) a stage that stores into its peers' receive area b waits until every peer has completed the stage that
+//      consumed what area b held before -- stage j + 1, j the previous boundary kept in b (in this execute, else the
+//      last one of the previous execute: back = 1).
+// `assign[i]` = buffer id holding the boundary between stage i and i + 1 (any ids; equal ids = same area).
+struct ExchangeWait {
+  int rank;   // rank of the user's Cartesian communicator to wait for
+  int back;   // 1: the target lies in the previous execute
+  int code;   // stages that rank must have completed
+};
+std::vector<ExchangeWait> exchange_waits(const Schedule &s, const std::vector<int> &assign, int stage);
+// does stage i hand its output to an exchange with more than one member?
+bool boundary_is_remote(const Schedule &s, int i);
+
 // Build the schedule of rank `pid`. Returns false (with sched->error) when the
 // configuration is legal for the reference but not yet supported here.
 bool build_schedule(const Problem &p, int pid, Schedule *sched);

@@ -140,6 +140,57 @@ size_t pfftb200_describe_kernels(int prec, int kind, int rnk_n, const ptrdiff_t 
   return j.size() + 1;
 }
 
+// TEST SUPPORT / introspection without a device: the device-side ordering of the p2p transport for rank `pid` --
+// per boundary whether an exchange fills it, which receive area (0 / 1, alternating) holds it and which ranks store
+// into it; per stage the progress values it waits for (exchange_waits, core.h).  tests/test_exchange_ordering.py
+// model-checks the protocol with these lists.
+size_t pfftb200_describe_exchange_ordering(int kind, int rnk_n, const ptrdiff_t *n, const ptrdiff_t *ni, const ptrdiff_t *no,
+                                           ptrdiff_t howmany, const ptrdiff_t *iblock, const ptrdiff_t *oblock, int rnk_pm,
+                                           const int *np, int pid, int sign, const int *kinds, const int *skip_trafos,
+                                           unsigned pfft_flags, char *buf, size_t buflen) {
+  Problem p;
+  fill_problem(&p, kind, rnk_n, n, ni, no, howmany, iblock, oblock, rnk_pm, np, sign, kinds, skip_trafos, pfft_flags);
+  Schedule s;
+  std::string j;
+  if (!build_schedule(p, pid, &s)) {
+    j = "{\"error\":\"" + s.error + "\"}";
+  } else {
+    const int nst = (int)s.stages.size(), nb = nst > 0 ? nst - 1 : 0;
+    std::vector<int> assign(nb);
+    for (int i = 0; i < nb; i++) assign[i] = i % 2;       // (plan.cu: assign_buffers with remote boundaries)
+    j = "{\"pid\":" + std::to_string(pid) + ",\"nstages\":" + std::to_string(nst) + ",\"remote\":[";
+    for (int i = 0; i < nb; i++) j += (i ? "," : "") + std::to_string(boundary_is_remote(s, i) ? 1 : 0);
+    j += "],\"buffer\":[";
+    for (int i = 0; i < nb; i++) j += (i ? "," : "") + std::to_string(assign[i]);
+    j += "],\"writers\":[";
+    for (int i = 0; i < nb; i++) {
+      j += i ? ",[" : "[";
+      if (boundary_is_remote(s, i)) {
+        const Exchange &x = s.exchanges[s.stages[i].exchange];
+        for (int q = 0; q < x.nparts; q++) j += (q ? "," : "") + std::to_string(s.groups[x.mesh_dim].members[q]);
+      } else {
+        j += std::to_string(pid);
+      }
+      j += "]";
+    }
+    j += "],\"waits\":[";
+    for (int i = 0; i < nst; i++) {
+      j += i ? ",[" : "[";
+      const std::vector<ExchangeWait> w = exchange_waits(s, assign, i);
+      for (size_t k = 0; k < w.size(); k++)
+        j += std::string(k ? "," : "") + "[" + std::to_string(w[k].rank) + "," + std::to_string(w[k].back) + "," + std::to_string(w[k].code) + "]";
+      j += "]";
+    }
+    j += "]}";
+  }
+  if (buf && buflen) {
+    size_t k = j.size() < buflen - 1 ? j.size() : buflen - 1;
+    memcpy(buf, j.data(), k);
+    buf[k] = 0;
+  }
+  return j.size() + 1;
+}
+
 const char *pfftb200_version(void) { return "pfft_b200 0.1 (sm_100a)"; }
 
 const char *pfftb200_last_error(void) { return last_error_ref().c_str(); }

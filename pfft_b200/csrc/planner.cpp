@@ -844,6 +844,37 @@ struct Builder {
 
 }  // namespace
 
+bool boundary_is_remote(const Schedule &s, int i) {
+  if (i < 0 || i + 1 >= (int)s.stages.size()) return false;
+  const int x = s.stages[i].exchange;
+  return x >= 0 && x < (int)s.exchanges.size() && s.exchanges[x].nparts > 1;
+}
+
+std::vector<ExchangeWait> exchange_waits(const Schedule &s, const std::vector<int> &assign, int i) {
+  std::vector<ExchangeWait> w;
+  auto add_group = [&](int xi, int back, int code) {
+    const Exchange &x = s.exchanges[xi];
+    for (int q = 0; q < x.nparts; q++)
+      if (q != x.me) w.push_back(ExchangeWait{s.groups[x.mesh_dim].members[q], back, code});
+  };
+  const int nb = (int)s.stages.size() - 1;      // boundaries
+  if (i > 0 && boundary_is_remote(s, i - 1)) add_group(s.stages[i - 1].exchange, 0, i);
+  if (i < nb && boundary_is_remote(s, i) && i < (int)assign.size()) {
+    const int b = assign[i];
+    int j = -1;
+    for (int k = i - 1; k >= 0; k--)
+      if (assign[k] == b) { j = k; break; }
+    if (j >= 0) {
+      add_group(s.stages[i].exchange, 0, j + 2);
+    } else {
+      for (int k = std::min(nb, (int)assign.size()) - 1; k >= 0; k--)
+        if (assign[k] == b) { j = k; break; }
+      add_group(s.stages[i].exchange, 1, j + 2);
+    }
+  }
+  return w;
+}
+
 int pow2_points_per_thread(int L) {
   // three radix passes at most: 64 -> 8*8, 128 -> 8*8*2, 256 -> 16*16, 512 -> 8*8*8, 1024 -> 16*16*4, ...
   return (L == 64 || L == 128 || L == 512) ? 8 : 16;

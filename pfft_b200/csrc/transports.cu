@@ -297,40 +297,19 @@ void transport_begin_execute(PlanBase *pl) {
   xch_begin_kernel<<<1, 1, 0, pl->stream>>>(pl->peers->flags);
 }
 
-// Device-side ordering in front of stage i:
-//  (a) its input was stored by the members of an exchange group: all of them must have completed stage i - 1;
-//  (b) it stores into its peers' receive area b: every peer must have completed the stage that consumed what
-//      area b held before -- stage j + 1, j the previous boundary kept in b (in this execute, else the last one
-//      of the previous execute).
+// Device-side ordering in front of stage i: the rule is exchange_waits (core.h / planner.cpp), a pure function of
+// the schedule that the CPU tests model-check (tests/test_exchange_ordering.py); here it becomes one wait kernel.
 void transport_wait_stage(PlanBase *pl, int i) {
-  const Schedule &s = pl->sched;
   PeerMap *pm = pl->peers;
+  const std::vector<ExchangeWait> waits = exchange_waits(pl->sched, pl->assign, i);
   WaitList w;
   w.n = 0;
-  auto add_group = [&](int xi, int back, unsigned code) {
-    const Exchange &x = s.exchanges[xi];
-    for (int q = 0; q < x.nparts; q++) {
-      if (q == x.me || w.n >= 2 * kMaxSeg) continue;
-      w.rank[w.n] = pm->member_rank[x.mesh_dim][q];
-      w.back[w.n] = back;
-      w.code[w.n] = code;
-      w.n++;
-    }
-  };
-  const int nb = (int)pl->boundary_remote.size();
-  if (i > 0 && pl->boundary_remote[i - 1]) add_group(s.stages[i - 1].exchange, 0, (unsigned)i);
-  if (i < nb && pl->boundary_remote[i]) {
-    const int b = pl->assign[i];
-    int j = -1;
-    for (int k = i - 1; k >= 0; k--)
-      if (pl->assign[k] == b) { j = k; break; }
-    if (j >= 0) {
-      add_group(s.stages[i].exchange, 0, (unsigned)(j + 2));
-    } else {
-      for (int k = nb - 1; k >= 0; k--)
-        if (pl->assign[k] == b) { j = k; break; }
-      add_group(s.stages[i].exchange, 1, (unsigned)(j + 2));
-    }
+  for (const ExchangeWait &e : waits) {
+    if (w.n >= 2 * kMaxSeg) break;
+    w.rank[w.n] = e.rank;
+    w.back[w.n] = e.back;
+    w.code[w.n] = (unsigned)e.code;
+    w.n++;
   }
   if (w.n > 0) xch_wait_kernel<<<1, 2 * kMaxSeg, 0, pl->stream>>>(pm->flags, w);
 }
