@@ -94,6 +94,7 @@ struct WaitList {
   int rank[2 * kMaxSeg];
   int back[2 * kMaxSeg];        // 1: the target lies in the previous execute
   unsigned code[2 * kMaxSeg];   // stages completed
+  unsigned long long timeout_ns;   // give up (loudly) after this long: PFFT_B200_WAIT_TIMEOUT_S, default 600 s
 };
 __global__ void xch_begin_kernel(unsigned *flags) { flags[0] += 1u; }
 __global__ void xch_signal_kernel(const unsigned *flags, unsigned *const *peer, int me, int np, unsigned code) {
@@ -116,12 +117,13 @@ __global__ void xch_wait_kernel(const unsigned *flags, const __grid_constant__ W
     if ((int)(v - target) >= 0) break;
     __nanosleep(200);
     if ((spins & 0xfff) == 0xfff) {
-      // a peer that never arrives (crashed rank, mismatched sequence of executes) must not hang the GPU for good
+      // a peer that never arrives (crashed rank, mismatched sequence of executes) must not hang the GPU for good --
+      // and must not be ignored either: the kernel traps, the next CUDA call of this rank reports the error
       unsigned long long t1;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > 60ull * 1000000000ull) {
+      if (t1 - t0 > w.timeout_ns) {
         printf("pfft_b200: gave up waiting for rank %d (progress %u, wanted %u)\n", w.rank[i], v, target);
-        break;
+        __trap();
       }
     }
   }
@@ -302,8 +304,14 @@ void transport_begin_execute(PlanBase *pl) {
 void transport_wait_stage(PlanBase *pl, int i) {
   PeerMap *pm = pl->peers;
   const std::vector<ExchangeWait> waits = exchange_waits(pl->sched, pl->assign, i);
+  static const unsigned long long timeout_ns = [] {
+    const char *e = getenv("PFFT_B200_WAIT_TIMEOUT_S");
+    const double sec = e ? atof(e) : 600.0;
+    return (unsigned long long)((sec > 0 ? sec : 600.0) * 1e9);
+  }();
   WaitList w;
   w.n = 0;
+  w.timeout_ns = timeout_ns;
   for (const ExchangeWait &e : waits) {
     if (w.n >= 2 * kMaxSeg) break;
     w.rank[w.n] = e.rank;
